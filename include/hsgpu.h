@@ -1,0 +1,195 @@
+/* hsgpu -- B200-native batched scan-to-map engine behind the hector_slam_lib API.
+ *
+ * Thin C ABI (plain pointers and sizes, no C++/torch types) over the sm_100a CUDA engine in
+ * tfe-slam-ucl_b200/csrc/. One engine lives on one GPU and holds `n_streams` independent
+ * hectorslam::HectorSlamProcessor states (multi-resolution log-odds grids, poses, update
+ * counters) resident in HBM. Every entry point cites the reference interface it replaces;
+ * HSL/ = src/hector_slam/hector_mapping/include/hector_slam_lib/ of the reference tree.
+ *
+ * Conventions
+ *   - every function returns an int status: HS_OK (0), a negative HS_ERR_* code, or a positive
+ *     cudaError_t value; hs_status_string() explains any of them. There is NO CPU fallback:
+ *     without a usable CUDA device hs_create fails with HS_ERR_NO_DEVICE / the CUDA error.
+ *   - "host" pointers are caller-owned host memory (pinned memory makes the copies asynchronous);
+ *     "device" pointers (the *_device entry points) are caller-owned device memory on the engine's GPU.
+ *   - calls on one engine must be serialised by the caller (the reference is not re-entrant either:
+ *     HSL/matcher/ScanMatcher.h keeps H/dTr as members). Different engines are independent.
+ *   - poses are (x [m], y [m], theta [rad]) in world coordinates; points are in level-0 map cells
+ *     relative to the sensor (what HectorMappingRos::rosLaserScanToDataContainer produces).
+ *   - 3x3 matrices are row-major.
+ */
+#ifndef HSGPU_H
+#define HSGPU_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HS_OK 0
+#define HS_ERR_INVALID_ARG (-1)
+#define HS_ERR_NO_DEVICE (-2)
+#define HS_ERR_OUT_OF_MEMORY (-3)
+#define HS_ERR_NOT_CONFIGURED (-4)
+
+#define HS_MAX_LEVELS 8
+#define HS_ALL_STREAMS (-1)
+
+typedef struct hs_engine hs_engine;
+
+/* Same 8-byte layout as LogOddsCell (HSL/map/GridMapLogOdds.h:37-103). */
+typedef struct { float logOddsVal; int32_t updateIndex; } hs_cell;
+
+/* Constructor arguments of HectorSlamProcessor (HSL/slam_main/HectorSlamProcessor.h:54-64) plus
+ * the batch geometry. Library defaults are applied as in the reference: update factors 0.4 / 0.6
+ * (HSL/map/GridMapLogOdds.h:117-118), map-update gate 0.4 m / 0.13 rad (HectorSlamProcessor.h:62-63). */
+typedef struct {
+  float map_resolution; /* mapResolution [m per level-0 cell] */
+  int32_t map_size_x;   /* mapSizeX [cells, level 0] */
+  int32_t map_size_y;   /* mapSizeY */
+  float start_x;        /* startCoords.x (fraction of the map, 0.5 = centre) */
+  float start_y;        /* startCoords.y */
+  int32_t levels;       /* multi_res_size, 1..HS_MAX_LEVELS */
+  int32_t n_streams;    /* independent processors held by this engine */
+  int32_t max_points;   /* capacity of one DataContainer (beams per scan) */
+  int32_t device;       /* CUDA device ordinal */
+} hs_config;
+
+/* ---- lifetime / configuration ---------------------------------------------------------- */
+
+/* HectorSlamProcessor ctor + MapRepMultiMap ctor (HSL/slam_main/MapRepMultiMap.h:48-72). */
+int hs_create(const hs_config* cfg, hs_engine** out);
+/* ~HectorSlamProcessor (HectorSlamProcessor.h:66-69). */
+int hs_destroy(hs_engine* e);
+/* HectorSlamProcessor::reset (HectorSlamProcessor.h:115-124); stream = HS_ALL_STREAMS or an index.
+ * As in the reference the per-grid update counters keep counting across resets. */
+int hs_reset(hs_engine* e, int stream);
+/* setUpdateFactorFree / setUpdateFactorOccupied (HectorSlamProcessor.h:136-137), all streams. */
+int hs_set_update_factor_free(hs_engine* e, float free_factor);
+int hs_set_update_factor_occupied(hs_engine* e, float occupied_factor);
+/* setMapUpdateMinDistDiff / setMapUpdateMinAngleDiff (HectorSlamProcessor.h:138-139), all streams. */
+int hs_set_map_update_min_dist_diff(hs_engine* e, float min_dist);
+int hs_set_map_update_min_angle_diff(hs_engine* e, float min_angle);
+/* getScaleToMap / getMapLevels (HectorSlamProcessor.h:128-130). */
+float hs_get_scale_to_map(const hs_engine* e);
+int hs_get_map_levels(const hs_engine* e);
+int hs_get_n_streams(const hs_engine* e);
+int hs_get_max_points(const hs_engine* e);
+/* GridMapBase::getSizeX/getSizeY/getCellLength of one level (HSL/map/GridMapBase.h:60-61,303-306). */
+int hs_get_level_dims(const hs_engine* e, int level, int* size_x, int* size_y, float* cell_length);
+/* Launch all work of this engine on an externally owned cudaStream_t (NULL = engine-owned stream). */
+int hs_set_cuda_stream(hs_engine* e, void* cuda_stream);
+/* Block until all work queued by this engine has finished. */
+int hs_synchronize(hs_engine* e);
+const char* hs_status_string(int status);
+
+/* ---- the hot path ------------------------------------------------------------------------ */
+
+/* HectorSlamProcessor::update (HectorSlamProcessor.h:71-113) for n streams in one launch sequence:
+ * MapRepMultiMap::matchData -> poseDifferenceLargerThan gate -> MapRepMultiMap::updateByScan.
+ *   stream_ids           [n] engine stream index of each slot, or NULL for 0..n-1 (ids must be distinct)
+ *   points               [n][max_points][2] DataContainer points (level-0 cells), only counts[i] used
+ *   counts               [n] DataContainer::getSize()
+ *   origos               [n][2] DataContainer::getOrigo(), or NULL for (0,0)
+ *   pose_hints           [n][3] poseHintWorld, or NULL to use each stream's last scan-match pose
+ *   map_without_matching [n] bool flags, or NULL for false
+ *   poses_out            [n][3] getLastScanMatchPose() after the update, or NULL
+ *   cov_out              [n][9] getLastScanMatchCovariance() (the last level-0 Hessian), or NULL
+ * Host variant: copies inputs H2D, runs, copies outputs D2H and returns when they are valid. */
+int hs_update_batch(hs_engine* e, int n, const int32_t* stream_ids, const float* points, const int32_t* counts,
+                    const float* origos, const float* pose_hints, const uint8_t* map_without_matching,
+                    float* poses_out, float* cov_out);
+/* Device variant: all pointers are device memory; asynchronous on the engine's stream; results stay
+ * in the engine (hs_get_poses / hs_get_covariances, or hs_device_pose_ptr). */
+int hs_update_batch_device(hs_engine* e, int n, const int32_t* stream_ids, const float* points, const int32_t* counts,
+                           const float* origos, const float* pose_hints, const uint8_t* map_without_matching);
+
+/* LaserScan ingestion (HectorMappingRos::rosLaserScanToDataContainer, src/hector_slam/hector_mapping/src/
+ * HectorMappingRos.cpp:483-507) fused in front of update: ranges [n][n_beams] -> points on device.
+ * hs_set_scan_geometry fixes sensor_msgs/LaserScan's angle_min, angle_increment, range_min, range_max. */
+int hs_set_scan_geometry(hs_engine* e, int n_beams, float angle_min, float angle_increment, float range_min, float range_max);
+int hs_update_batch_ranges(hs_engine* e, int n, const int32_t* stream_ids, const float* ranges,
+                           const float* pose_hints, const uint8_t* map_without_matching, float* poses_out, float* cov_out);
+int hs_update_batch_ranges_device(hs_engine* e, int n, const int32_t* stream_ids, const float* ranges,
+                                  const float* pose_hints, const uint8_t* map_without_matching);
+/* Host helper with the same arithmetic (for callers that want DataContainer points). Returns the count. */
+int hs_scan_to_points_host(const float* ranges, int n_beams, float angle_min, float angle_increment,
+                           float range_min, float range_max, float scale_to_map, float* points_out);
+
+/* getLastScanMatchPose / getLastScanMatchCovariance (HectorSlamProcessor.h:126-127) of streams
+ * [first, first+n) into host memory. hs_get_last_map_update_poses exposes lastMapUpdatePose. */
+int hs_get_poses(hs_engine* e, int first, int n, float* poses_out);
+int hs_get_covariances(hs_engine* e, int first, int n, float* cov_out);
+int hs_get_last_map_update_poses(hs_engine* e, int first, int n, float* poses_out);
+/* Device-resident [n_streams][3] array of last scan-match poses (valid for the engine's lifetime). */
+const float* hs_device_pose_ptr(const hs_engine* e);
+
+/* ---- single-function entry points (parity tests, relocalisation, teacher forcing) ------- */
+
+/* OccGridMapUtil::getCompleteHessianDerivs (HSL/map/OccGridMapUtil.h:64-104) of ONE stream's level for
+ * n_poses pose hypotheses (MAP coordinates of that level) over one point set already scaled to that
+ * level: H9 [n_poses][9], dTr3 [n_poses][3]. All host pointers. */
+int hs_hessian_derivs_batch(hs_engine* e, int stream, int level, const float* poses_map, int n_poses,
+                            const float* points, int n_points, float* H9, float* dTr3);
+/* MapRepMultiMap::matchData only (HSL/slam_main/MapRepMultiMap.h:116-132): no gate, no integration,
+ * last scan-match pose/covariance are updated like update() would. Host pointers. */
+int hs_match_batch(hs_engine* e, int n, const int32_t* stream_ids, const float* points, const int32_t* counts,
+                   const float* origos, const float* pose_hints, float* poses_out, float* cov_out);
+/* MapRepMultiMap::updateByScan + onMapUpdated (MapRepMultiMap.h:107-114,134-147) with caller-given
+ * (teacher-forced) world poses: coarse-level containers are first refreshed from `points` exactly as
+ * matchData's setFrom would (MapRepMultiMap.h:127). Does not touch lastMapUpdatePose. Host pointers. */
+int hs_raycast_batch(hs_engine* e, int n, const int32_t* stream_ids, const float* points, const int32_t* counts,
+                     const float* origos, const float* poses_world);
+
+/* ---- map access --------------------------------------------------------------------------- */
+
+/* getGridMap(level) contents (HectorSlamProcessor.h:131): sx*sy cells, row-major cell[y*sx + x]. */
+int hs_download_level(hs_engine* e, int stream, int level, hs_cell* cells_out);
+int hs_upload_level(hs_engine* e, int stream, int level, const hs_cell* cells_in);
+/* GridMapBase::getUpdateIndex (HSL/map/GridMapBase.h:329). */
+int hs_get_update_index(hs_engine* e, int stream, int level, int* update_index_out);
+/* The occupancy classification HectorMappingRos::publishMap performs per cell (HectorMappingRos.cpp:447-470):
+ * -1 unknown, 0 free, 100 occupied; sx*sy int8 values. */
+int hs_classify_level(hs_engine* e, int stream, int level, int8_t* occupancy_out);
+
+/* ---- bookkeeping -------------------------------------------------------------------------- */
+
+typedef struct {
+  uint64_t updates;          /* stream-updates processed (scans matched or passed through) */
+  uint64_t integrations;     /* stream-updates that passed the gate and were ray-cast into the maps */
+  uint64_t angle_clamps;     /* Gauss-Newton steps whose rotation was clamped to +-0.2 rad
+                                (the reference prints "SearchDir angle change too large", ScanMatcher.h:211,214) */
+  uint64_t kernel_launches;  /* CUDA kernels launched by this engine so far */
+  uint64_t h2d_bytes, d2h_bytes;
+} hs_stats;
+int hs_get_stats(hs_engine* e, hs_stats* out);
+
+/* ---- deterministic synthetic scan streams (host code) ------------- */
+
+typedef struct {
+  int32_t n_beams;
+  float angle_min, angle_increment;
+  float range_min, range_max;
+  float noise_sigma;       /* Gaussian range noise [m] */
+  float room_w, room_h;    /* axis-aligned room centred at the origin [m] */
+  int32_t n_boxes;         /* axis-aligned box obstacles */
+  float box_min, box_max;  /* box edge length range [m] */
+  float traj_rx, traj_ry;  /* ellipse radii of the closed-loop trajectory [m] */
+  int32_t traj_period;     /* scans per loop */
+} hs_scene_config;
+
+#define HS_SCENE_RPLIDAR_ROOM 0 /* 360 beams 0..359 deg, 0.15-12 m, 10 m x 8 m room, 6 boxes (configs 1,2,5) */
+#define HS_SCENE_HIRES_HALL 1   /* 1440 beams, 30 m, 40 m x 30 m hall, 12 boxes (config 3) */
+int hs_scene_preset(int preset, hs_scene_config* out);
+/* ranges [n_scans][n_streams][n_beams] for streams seed0 + s (s in [0, n_streams)) and scans
+ * [first_scan, first_scan+n_scans); truth_poses [n_scans][n_streams][3] (relative to each stream's
+ * first pose) or NULL. Deterministic in (cfg, seed, scan, beam); `threads` host threads. */
+int hs_scangen_batch(const hs_scene_config* cfg, uint64_t seed0, int n_streams, int first_scan, int n_scans,
+                     float* ranges, float* truth_poses, int threads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HSGPU_H */
