@@ -72,6 +72,9 @@ int hs_set_update_factor_occupied(hs_engine* e, float occupied_factor);
 /* setMapUpdateMinDistDiff / setMapUpdateMinAngleDiff (HectorSlamProcessor.h:138-139), all streams. */
 int hs_set_map_update_min_dist_diff(hs_engine* e, float min_dist);
 int hs_set_map_update_min_angle_diff(hs_engine* e, float min_angle);
+/* Debug/parity switch: accumulate the Hessian and gradient sums in the reference's sequential point order
+ * (OccGridMapUtil.h:76-98) instead of per-lane partial sums + warp butterfly. Bitwise CPU-identical, slower. */
+int hs_set_strict_summation(hs_engine* e, int on);
 /* getScaleToMap / getMapLevels (HectorSlamProcessor.h:128-130). */
 float hs_get_scale_to_map(const hs_engine* e);
 int hs_get_map_levels(const hs_engine* e);
@@ -163,8 +166,20 @@ typedef struct {
                                 (the reference prints "SearchDir angle change too large", ScanMatcher.h:211,214) */
   uint64_t kernel_launches;  /* CUDA kernels launched by this engine so far */
   uint64_t h2d_bytes, d2h_bytes;
+  uint64_t cell_visits;      /* sum over integrated levels and valid beams of max(|dx|,|dy|) + 1 grid cells
+                                (the ray-caster's algorithmic work) */
 } hs_stats;
 int hs_get_stats(hs_engine* e, hs_stats* out);
+
+/* Per-kernel device time, measured with CUDA events recorded on the launching stream around every hot-path
+ * kernel while enabled. Index: 0 k_scan_to_points, 1 k_match, 2 k_raycast. */
+typedef struct {
+  double ms[3];
+  uint64_t launches[3];
+} hs_kernel_times;
+int hs_profile_enable(hs_engine* e, int on);
+/* Waits for the stream, sums the elapsed time per kernel since the last collect/enable, and clears the log. */
+int hs_profile_collect(hs_engine* e, hs_kernel_times* out);
 
 /* ---- deterministic synthetic scan streams (host code) ------------- */
 

@@ -1,0 +1,372 @@
+"""hsgpu -- B200-native batched scan-to-map engine behind the hector_slam_lib API.
+
+This Python module is only a ctypes binding over the C ABI in ``include/hsgpu.h`` (the product is the
+CUDA engine in ``csrc/`` built into ``libhsgpu.so``); it exists for the test-suite and ``bench.py``.
+There is no Python or CPU implementation of the hot path here: if ``libhsgpu.so`` is missing the import
+of the library fails loudly, and without a CUDA device ``Engine(...)`` raises ``HsError``.
+
+Reference interface mirrored: ``hectorslam::HectorSlamProcessor``
+(src/hector_slam/hector_mapping/include/hector_slam_lib/slam_main/HectorSlamProcessor.h:50-154).
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhsgpu.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+HS_OK = 0
+HS_ERR_INVALID_ARG = -1
+HS_ERR_NO_DEVICE = -2
+HS_ERR_OUT_OF_MEMORY = -3
+HS_ERR_NOT_CONFIGURED = -4
+HS_ALL_STREAMS = -1
+SCENE_RPLIDAR_ROOM = 0
+SCENE_HIRES_HALL = 1
+
+CELL_DTYPE = np.dtype([("logOddsVal", np.float32), ("updateIndex", np.int32)])
+
+
+class HsError(RuntimeError):
+    def __init__(self, status, what):
+        self.status = status
+        super().__init__("%s failed: %s (status %d)" % (what, status_string(status), status))
+
+
+class HsConfig(ctypes.Structure):
+    _fields_ = [("map_resolution", ctypes.c_float), ("map_size_x", ctypes.c_int32), ("map_size_y", ctypes.c_int32),
+                ("start_x", ctypes.c_float), ("start_y", ctypes.c_float), ("levels", ctypes.c_int32),
+                ("n_streams", ctypes.c_int32), ("max_points", ctypes.c_int32), ("device", ctypes.c_int32)]
+
+
+class HsStats(ctypes.Structure):
+    _fields_ = [("updates", ctypes.c_uint64), ("integrations", ctypes.c_uint64), ("angle_clamps", ctypes.c_uint64),
+                ("kernel_launches", ctypes.c_uint64), ("h2d_bytes", ctypes.c_uint64), ("d2h_bytes", ctypes.c_uint64),
+                ("cell_visits", ctypes.c_uint64)]
+
+
+class HsKernelTimes(ctypes.Structure):
+    _fields_ = [("ms", ctypes.c_double * 3), ("launches", ctypes.c_uint64 * 3)]
+
+
+KERNEL_NAMES = ("k_scan_to_points", "k_match", "k_raycast")
+
+
+class SceneConfig(ctypes.Structure):
+    _fields_ = [("n_beams", ctypes.c_int32), ("angle_min", ctypes.c_float), ("angle_increment", ctypes.c_float),
+                ("range_min", ctypes.c_float), ("range_max", ctypes.c_float), ("noise_sigma", ctypes.c_float),
+                ("room_w", ctypes.c_float), ("room_h", ctypes.c_float), ("n_boxes", ctypes.c_int32),
+                ("box_min", ctypes.c_float), ("box_max", ctypes.c_float), ("traj_rx", ctypes.c_float),
+                ("traj_ry", ctypes.c_float), ("traj_period", ctypes.c_int32)]
+
+
+def build(verbose=False):
+    """Compile libhsgpu.so for sm_100a (nvcc cross-compiles without a GPU)."""
+    res = subprocess.run(["make", "-C", CSRC], capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        print(res.stdout)
+        print(res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError("building libhsgpu.so failed")
+    return LIB_PATH
+
+
+_lib = None
+_P = ctypes.c_void_p
+_I = ctypes.c_int
+_F = ctypes.c_float
+
+
+def lib():
+    """The loaded C-ABI library. Raises if it has not been built: there is no fallback path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("libhsgpu.so is missing (%s): run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "or `make -C tfe-slam-ucl_b200/csrc`; hsgpu has no CPU fallback" % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    sig = {
+        "hs_create": (_I, [_P, _P]), "hs_destroy": (_I, [_P]), "hs_reset": (_I, [_P, _I]),
+        "hs_set_update_factor_free": (_I, [_P, _F]), "hs_set_update_factor_occupied": (_I, [_P, _F]),
+        "hs_set_map_update_min_dist_diff": (_I, [_P, _F]), "hs_set_map_update_min_angle_diff": (_I, [_P, _F]),
+        "hs_set_strict_summation": (_I, [_P, _I]),
+        "hs_get_scale_to_map": (_F, [_P]), "hs_get_map_levels": (_I, [_P]), "hs_get_n_streams": (_I, [_P]),
+        "hs_get_max_points": (_I, [_P]), "hs_get_level_dims": (_I, [_P, _I, _P, _P, _P]),
+        "hs_set_cuda_stream": (_I, [_P, _P]), "hs_synchronize": (_I, [_P]), "hs_status_string": (ctypes.c_char_p, [_I]),
+        "hs_update_batch": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
+        "hs_update_batch_device": (_I, [_P, _I, _P, _P, _P, _P, _P, _P]),
+        "hs_set_scan_geometry": (_I, [_P, _I, _F, _F, _F, _F]),
+        "hs_update_batch_ranges": (_I, [_P, _I, _P, _P, _P, _P, _P, _P]),
+        "hs_update_batch_ranges_device": (_I, [_P, _I, _P, _P, _P, _P]),
+        "hs_scan_to_points_host": (_I, [_P, _I, _F, _F, _F, _F, _F, _P]),
+        "hs_get_poses": (_I, [_P, _I, _I, _P]), "hs_get_covariances": (_I, [_P, _I, _I, _P]),
+        "hs_get_last_map_update_poses": (_I, [_P, _I, _I, _P]), "hs_device_pose_ptr": (_P, [_P]),
+        "hs_hessian_derivs_batch": (_I, [_P, _I, _I, _P, _I, _P, _I, _P, _P]),
+        "hs_match_batch": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _P]),
+        "hs_raycast_batch": (_I, [_P, _I, _P, _P, _P, _P, _P]),
+        "hs_download_level": (_I, [_P, _I, _I, _P]), "hs_upload_level": (_I, [_P, _I, _I, _P]),
+        "hs_get_update_index": (_I, [_P, _I, _I, _P]), "hs_classify_level": (_I, [_P, _I, _I, _P]),
+        "hs_get_stats": (_I, [_P, _P]),
+        "hs_profile_enable": (_I, [_P, _I]), "hs_profile_collect": (_I, [_P, _P]),
+        "hs_scene_preset": (_I, [_I, _P]),
+        "hs_scangen_batch": (_I, [_P, ctypes.c_uint64, _I, _I, _I, _P, _P, _I]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+def status_string(status):
+    return lib().hs_status_string(int(status)).decode()
+
+
+def _check(status, what):
+    if status != HS_OK:
+        raise HsError(status, what)
+
+
+def _arr(a, dtype, shape=None):
+    if a is None:
+        return None
+    a = np.ascontiguousarray(a, dtype=dtype)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+# ---- synthetic scan streams (host) -----------------------------------------------------------------
+
+def scene_preset(preset=SCENE_RPLIDAR_ROOM):
+    sc = SceneConfig()
+    _check(lib().hs_scene_preset(preset, ctypes.byref(sc)), "hs_scene_preset")
+    return sc
+
+
+def scangen_batch(scene, seed0, n_streams, first_scan, n_scans, threads=None, truth=True, out=None):
+    """ranges [n_scans][n_streams][n_beams] (and truth poses [n_scans][n_streams][3])."""
+    threads = threads or (os.cpu_count() or 1)
+    ranges = out if out is not None else np.empty((n_scans, n_streams, scene.n_beams), np.float32)
+    tr = np.empty((n_scans, n_streams, 3), np.float32) if truth else None
+    _check(lib().hs_scangen_batch(ctypes.byref(scene), seed0, n_streams, first_scan, n_scans, ranges.ctypes.data,
+                                  _ptr(tr), threads), "hs_scangen_batch")
+    return ranges, tr
+
+
+def scan_to_points_host(ranges, scene, scale_to_map, max_points=None):
+    """rosLaserScanToDataContainer over a [..., n_beams] array -> (points [..., max_points, 2], counts [...])."""
+    ranges = np.ascontiguousarray(ranges, np.float32)
+    lead = ranges.shape[:-1]
+    nb = ranges.shape[-1]
+    mp = max_points or nb
+    flat = ranges.reshape(-1, nb)
+    pts = np.zeros((flat.shape[0], mp, 2), np.float32)
+    cnt = np.zeros(flat.shape[0], np.int32)
+    tmp = np.zeros((nb, 2), np.float32)
+    fn = lib().hs_scan_to_points_host
+    for i in range(flat.shape[0]):
+        c = fn(flat[i].ctypes.data, nb, scene.angle_min, scene.angle_increment, scene.range_min, scene.range_max,
+               scale_to_map, tmp.ctypes.data)
+        c = min(c, mp)
+        pts[i, :c] = tmp[:c]
+        cnt[i] = c
+    return pts.reshape(lead + (mp, 2)), cnt.reshape(lead)
+
+
+# ---- the engine ------------------------------------------------------------------------------------
+
+class Engine:
+    """n_streams independent HectorSlamProcessor states on one GPU."""
+
+    def __init__(self, map_resolution=0.05, map_size_x=1024, map_size_y=1024, start=(0.5, 0.5), levels=3, n_streams=1,
+                 max_points=360, device=0):
+        self._h = ctypes.c_void_p()
+        self.cfg = HsConfig(map_resolution, map_size_x, map_size_y, start[0], start[1], levels, n_streams, max_points, device)
+        _check(lib().hs_create(ctypes.byref(self.cfg), ctypes.byref(self._h)), "hs_create")
+        self.n_streams = n_streams
+        self.max_points = max_points
+        self.levels = levels
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().hs_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # configuration (HectorSlamProcessor.h:136-139)
+    def set_update_factor_free(self, f): _check(lib().hs_set_update_factor_free(self._h, f), "hs_set_update_factor_free")
+    def set_update_factor_occupied(self, f): _check(lib().hs_set_update_factor_occupied(self._h, f), "hs_set_update_factor_occupied")
+    def set_map_update_min_dist_diff(self, d): _check(lib().hs_set_map_update_min_dist_diff(self._h, d), "hs_set_map_update_min_dist_diff")
+    def set_map_update_min_angle_diff(self, a): _check(lib().hs_set_map_update_min_angle_diff(self._h, a), "hs_set_map_update_min_angle_diff")
+    def set_strict_summation(self, on): _check(lib().hs_set_strict_summation(self._h, int(on)), "hs_set_strict_summation")
+    def set_cuda_stream(self, handle): _check(lib().hs_set_cuda_stream(self._h, handle), "hs_set_cuda_stream")
+    def synchronize(self): _check(lib().hs_synchronize(self._h), "hs_synchronize")
+    def reset(self, stream=HS_ALL_STREAMS): _check(lib().hs_reset(self._h, stream), "hs_reset")
+    def scale_to_map(self): return lib().hs_get_scale_to_map(self._h)
+    def map_levels(self): return lib().hs_get_map_levels(self._h)
+
+    def level_dims(self, level):
+        sx, sy, cl = ctypes.c_int(), ctypes.c_int(), ctypes.c_float()
+        _check(lib().hs_get_level_dims(self._h, level, ctypes.byref(sx), ctypes.byref(sy), ctypes.byref(cl)), "hs_get_level_dims")
+        return sx.value, sy.value, cl.value
+
+    def set_scan_geometry(self, n_beams, angle_min, angle_increment, range_min, range_max):
+        _check(lib().hs_set_scan_geometry(self._h, n_beams, angle_min, angle_increment, range_min, range_max), "hs_set_scan_geometry")
+
+    # the hot path
+    def update_batch(self, points, counts, origos=None, pose_hints=None, map_without_matching=None, stream_ids=None,
+                     want_cov=True):
+        counts = _arr(counts, np.int32)
+        n = counts.shape[0]
+        points = _arr(points, np.float32, (n, self.max_points, 2))
+        origos = _arr(origos, np.float32, (n, 2))
+        pose_hints = _arr(pose_hints, np.float32, (n, 3))
+        flags = _arr(map_without_matching, np.uint8, (n,))
+        ids = _arr(stream_ids, np.int32, (n,))
+        poses = np.empty((n, 3), np.float32)
+        cov = np.empty((n, 9), np.float32) if want_cov else None
+        _check(lib().hs_update_batch(self._h, n, _ptr(ids), points.ctypes.data, counts.ctypes.data, _ptr(origos),
+                                     _ptr(pose_hints), _ptr(flags), poses.ctypes.data, _ptr(cov)), "hs_update_batch")
+        return poses, (cov.reshape(n, 3, 3) if want_cov else None)
+
+    def update_batch_raw(self, n, points_ptr, counts_ptr, poses_out_ptr, origos_ptr=None, hints_ptr=None, flags_ptr=None,
+                         ids_ptr=None, cov_out_ptr=None):
+        """hs_update_batch with raw host addresses (pinned buffers in bench.py)."""
+        _check(lib().hs_update_batch(self._h, n, ids_ptr, points_ptr, counts_ptr, origos_ptr, hints_ptr, flags_ptr,
+                                     poses_out_ptr, cov_out_ptr), "hs_update_batch")
+
+    def update_batch_device(self, n, points_dptr, counts_dptr, origos_dptr=None, hints_dptr=None, flags_dptr=None, ids_dptr=None):
+        _check(lib().hs_update_batch_device(self._h, n, ids_dptr, points_dptr, counts_dptr, origos_dptr, hints_dptr, flags_dptr),
+               "hs_update_batch_device")
+
+    def update_batch_ranges(self, ranges, pose_hints=None, map_without_matching=None, stream_ids=None, want_cov=True):
+        ranges = np.ascontiguousarray(ranges, np.float32)
+        n = ranges.shape[0]
+        pose_hints = _arr(pose_hints, np.float32, (n, 3))
+        flags = _arr(map_without_matching, np.uint8, (n,))
+        ids = _arr(stream_ids, np.int32, (n,))
+        poses = np.empty((n, 3), np.float32)
+        cov = np.empty((n, 9), np.float32) if want_cov else None
+        _check(lib().hs_update_batch_ranges(self._h, n, _ptr(ids), ranges.ctypes.data, _ptr(pose_hints), _ptr(flags),
+                                            poses.ctypes.data, _ptr(cov)), "hs_update_batch_ranges")
+        return poses, (cov.reshape(n, 3, 3) if want_cov else None)
+
+    def update_batch_ranges_raw(self, n, ranges_ptr, poses_out_ptr, hints_ptr=None, flags_ptr=None, ids_ptr=None, cov_out_ptr=None):
+        _check(lib().hs_update_batch_ranges(self._h, n, ids_ptr, ranges_ptr, hints_ptr, flags_ptr, poses_out_ptr, cov_out_ptr),
+               "hs_update_batch_ranges")
+
+    def update_batch_ranges_device(self, n, ranges_dptr, hints_dptr=None, flags_dptr=None, ids_dptr=None):
+        _check(lib().hs_update_batch_ranges_device(self._h, n, ids_dptr, ranges_dptr, hints_dptr, flags_dptr),
+               "hs_update_batch_ranges_device")
+
+    def match_batch(self, points, counts, origos=None, pose_hints=None, stream_ids=None):
+        counts = _arr(counts, np.int32)
+        n = counts.shape[0]
+        points = _arr(points, np.float32, (n, self.max_points, 2))
+        origos = _arr(origos, np.float32, (n, 2))
+        pose_hints = _arr(pose_hints, np.float32, (n, 3))
+        ids = _arr(stream_ids, np.int32, (n,))
+        poses = np.empty((n, 3), np.float32)
+        cov = np.empty((n, 9), np.float32)
+        _check(lib().hs_match_batch(self._h, n, _ptr(ids), points.ctypes.data, counts.ctypes.data, _ptr(origos),
+                                    _ptr(pose_hints), poses.ctypes.data, cov.ctypes.data), "hs_match_batch")
+        return poses, cov.reshape(n, 3, 3)
+
+    def raycast_batch(self, points, counts, poses_world, origos=None, stream_ids=None):
+        counts = _arr(counts, np.int32)
+        n = counts.shape[0]
+        points = _arr(points, np.float32, (n, self.max_points, 2))
+        origos = _arr(origos, np.float32, (n, 2))
+        poses_world = _arr(poses_world, np.float32, (n, 3))
+        ids = _arr(stream_ids, np.int32, (n,))
+        _check(lib().hs_raycast_batch(self._h, n, _ptr(ids), points.ctypes.data, counts.ctypes.data, _ptr(origos),
+                                      poses_world.ctypes.data), "hs_raycast_batch")
+
+    def hessian_derivs_batch(self, stream, level, poses_map, points):
+        poses_map = _arr(poses_map, np.float32).reshape(-1, 3)
+        points = _arr(points, np.float32).reshape(-1, 2)
+        n = poses_map.shape[0]
+        H = np.empty((n, 9), np.float32)
+        d = np.empty((n, 3), np.float32)
+        _check(lib().hs_hessian_derivs_batch(self._h, stream, level, poses_map.ctypes.data, n, points.ctypes.data,
+                                             points.shape[0], H.ctypes.data, d.ctypes.data), "hs_hessian_derivs_batch")
+        return H.reshape(n, 3, 3), d
+
+    # state access
+    def poses(self, first=0, n=None):
+        n = self.n_streams - first if n is None else n
+        out = np.empty((n, 3), np.float32)
+        _check(lib().hs_get_poses(self._h, first, n, out.ctypes.data), "hs_get_poses")
+        return out
+
+    def covariances(self, first=0, n=None):
+        n = self.n_streams - first if n is None else n
+        out = np.empty((n, 9), np.float32)
+        _check(lib().hs_get_covariances(self._h, first, n, out.ctypes.data), "hs_get_covariances")
+        return out.reshape(n, 3, 3)
+
+    def last_map_update_poses(self, first=0, n=None):
+        n = self.n_streams - first if n is None else n
+        out = np.empty((n, 3), np.float32)
+        _check(lib().hs_get_last_map_update_poses(self._h, first, n, out.ctypes.data), "hs_get_last_map_update_poses")
+        return out
+
+    def device_pose_ptr(self):
+        return lib().hs_device_pose_ptr(self._h)
+
+    def download_level(self, stream, level):
+        sx, sy, _ = self.level_dims(level)
+        out = np.empty(sx * sy, CELL_DTYPE)
+        _check(lib().hs_download_level(self._h, stream, level, out.ctypes.data), "hs_download_level")
+        return out
+
+    def upload_level(self, stream, level, cells):
+        cells = np.ascontiguousarray(cells, CELL_DTYPE)
+        sx, sy, _ = self.level_dims(level)
+        assert cells.size == sx * sy
+        _check(lib().hs_upload_level(self._h, stream, level, cells.ctypes.data), "hs_upload_level")
+
+    def update_index(self, stream, level=0):
+        v = ctypes.c_int()
+        _check(lib().hs_get_update_index(self._h, stream, level, ctypes.byref(v)), "hs_get_update_index")
+        return v.value
+
+    def classify_level(self, stream, level):
+        sx, sy, _ = self.level_dims(level)
+        out = np.empty(sx * sy, np.int8)
+        _check(lib().hs_classify_level(self._h, stream, level, out.ctypes.data), "hs_classify_level")
+        return out
+
+    def profile_enable(self, on=True):
+        _check(lib().hs_profile_enable(self._h, int(on)), "hs_profile_enable")
+
+    def profile_collect(self):
+        t = HsKernelTimes()
+        _check(lib().hs_profile_collect(self._h, ctypes.byref(t)), "hs_profile_collect")
+        return {KERNEL_NAMES[i]: {"ms": t.ms[i], "launches": int(t.launches[i])} for i in range(3)}
+
+    def stats(self):
+        s = HsStats()
+        _check(lib().hs_get_stats(self._h, ctypes.byref(s)), "hs_get_stats")
+        return {k: getattr(s, k) for k, _ in HsStats._fields_}

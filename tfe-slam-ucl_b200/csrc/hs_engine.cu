@@ -1,0 +1,723 @@
+// hsgpu engine: host side of the C ABI declared in include/hsgpu.h. Owns the device memory of all streams
+// (grids resident in HBM for the engine's lifetime) and sequences the kernels of hs_kernels.cuh on one CUDA
+// stream. There is deliberately no CPU implementation of the hot path in this library: every entry point
+// either runs the CUDA kernels or returns an error status.
+#include <cuda_runtime.h>
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "hs_kernels.cuh"
+#include "hsgpu.h"
+
+struct hs_engine {
+  hs_config cfg;
+  HsParams P;
+  int device;
+  cudaStream_t own_stream;
+  cudaStream_t stream;
+  // staging (device) for the host-pointer entry points
+  float* d_points;
+  int32_t* d_counts;
+  float* d_origos;
+  float* d_hints;
+  uint8_t* d_flags;
+  int32_t* d_ids;
+  float* d_ranges;
+  float* d_out;      // [n_streams][9] gather scratch
+  float2* d_beam_cs; // scan geometry
+  int n_beams;
+  float range_min, max_range_for_container, angle_min, angle_increment, range_max;
+  // misc scratch for single-function entry points
+  void* d_scratch;
+  size_t scratch_bytes;
+  // bookkeeping
+  uint64_t updates, launches, h2d_bytes, d2h_bytes;
+  float free_factor, occ_factor;
+  // optional per-kernel timing with CUDA events on the launching stream (hs_profile_*)
+  int profiling;
+  std::vector<cudaEvent_t>* prof_events;  // pairs: start, stop
+  std::vector<int>* prof_ids;
+  size_t prof_used;
+};
+
+enum { HS_K_SCAN_TO_POINTS = 0, HS_K_MATCH = 1, HS_K_RAYCAST = 2, HS_K_COUNT = 3 };
+
+struct ProfScope {
+  hs_engine* e;
+  cudaEvent_t stop;
+  ProfScope(hs_engine* eng, int id) : e(eng), stop(nullptr) {
+    if (!e->profiling) return;
+    if (e->prof_used + 2 > e->prof_events->size()) {
+      cudaEvent_t a, b;
+      if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+      e->prof_events->push_back(a);
+      e->prof_events->push_back(b);
+    }
+    cudaEvent_t start = (*e->prof_events)[e->prof_used];
+    stop = (*e->prof_events)[e->prof_used + 1];
+    e->prof_used += 2;
+    e->prof_ids->push_back(id);
+    cudaEventRecord(start, e->stream);
+  }
+  ~ProfScope() {
+    if (stop) cudaEventRecord(stop, e->stream);
+  }
+};
+
+#define HS_CK(call)                                  \
+  do {                                               \
+    cudaError_t err__ = (call);                      \
+    if (err__ != cudaSuccess) return (int)err__;     \
+  } while (0)
+
+static inline int hs_launch_check(hs_engine* e) {
+  e->launches++;
+  cudaError_t err = cudaGetLastError();
+  return err == cudaSuccess ? HS_OK : (int)err;
+}
+#define HS_LAUNCHED(e)                 \
+  do {                                 \
+    int st__ = hs_launch_check(e);     \
+    if (st__ != HS_OK) return st__;    \
+  } while (0)
+
+static int warp_grid(int n_warps, int threads) { return (n_warps * 32 + threads - 1) / threads; }
+
+// GridMapLogOddsFunctions::probToLogOdds (HSL/map/GridMapLogOdds.h:198-203), host libm like the reference.
+static float prob_to_log_odds(float prob) {
+  volatile float odds = prob / (1.0f - prob);
+  return logf(odds);
+}
+
+// GridMapBase::setMapTransformation (HSL/map/GridMapBase.h:265-280): Scaling(s)*Translation(off) and its
+// affine inverse with Eigen 3.3's 2x2 inverse ((1/det) * adjugate, t' = (-Linv) t), fp32, unfused.
+static void level_transform(HsLevel* L, float offx, float offy, float cell_length) {
+  volatile float s = 1.0f / cell_length;
+  volatile float tmx = s * offx, tmy = s * offy;
+  volatile float m00 = s, m01 = 0.0f, m10 = 0.0f, m11 = s;
+  volatile float p0 = m00 * m11, p1 = m10 * m01;
+  volatile float det = p0 - p1;
+  volatile float invdet = 1.0f / det;
+  volatile float i00 = m11 * invdet, i10 = -m10 * invdet, i01 = -m01 * invdet, i11 = m00 * invdet;
+  volatile float q0 = (-i00) * tmx, q1 = (-i01) * tmy, q2 = (-i10) * tmx, q3 = (-i11) * tmy;
+  volatile float twx = q0 + q1, twy = q2 + q3;
+  (void)i11;
+  L->scale = s;
+  L->tmx = tmx;
+  L->tmy = tmy;
+  L->a = i00;
+  L->twx = twx;
+  L->twy = twy;
+}
+
+static int ensure_scratch(hs_engine* e, size_t bytes) {
+  if (bytes <= e->scratch_bytes) return HS_OK;
+  if (e->d_scratch) cudaFree(e->d_scratch);
+  e->d_scratch = nullptr;
+  e->scratch_bytes = 0;
+  HS_CK(cudaMalloc(&e->d_scratch, bytes));
+  e->scratch_bytes = bytes;
+  return HS_OK;
+}
+
+extern "C" {
+
+const char* hs_status_string(int status) {
+  switch (status) {
+    case HS_OK: return "ok";
+    case HS_ERR_INVALID_ARG: return "invalid argument";
+    case HS_ERR_NO_DEVICE: return "no usable CUDA device (hsgpu has no CPU fallback)";
+    case HS_ERR_OUT_OF_MEMORY: return "out of memory";
+    case HS_ERR_NOT_CONFIGURED: return "scan geometry not set (hs_set_scan_geometry)";
+    default: break;
+  }
+  if (status > 0) return cudaGetErrorString((cudaError_t)status);
+  return "unknown hsgpu status";
+}
+
+int hs_create(const hs_config* cfg, hs_engine** out) {
+  if (!cfg || !out) return HS_ERR_INVALID_ARG;
+  *out = nullptr;
+  if (cfg->levels < 1 || cfg->levels > HS_MAX_LEVELS || cfg->n_streams < 1 || cfg->max_points < 1 ||
+      cfg->map_size_x < 2 || cfg->map_size_y < 2 || !(cfg->map_resolution > 0.0f))
+    return HS_ERR_INVALID_ARG;
+  if ((cfg->map_size_x >> (cfg->levels - 1)) < 2 || (cfg->map_size_y >> (cfg->levels - 1)) < 2) return HS_ERR_INVALID_ARG;
+  int n_dev = 0;
+  cudaError_t derr = cudaGetDeviceCount(&n_dev);
+  if (derr != cudaSuccess || n_dev <= 0) return HS_ERR_NO_DEVICE;
+  if (cfg->device < 0 || cfg->device >= n_dev) return HS_ERR_INVALID_ARG;
+  HS_CK(cudaSetDevice(cfg->device));
+
+  hs_engine* e = new (std::nothrow) hs_engine();
+  if (!e) return HS_ERR_OUT_OF_MEMORY;
+  memset(e, 0, sizeof(*e));
+  e->prof_events = new std::vector<cudaEvent_t>();
+  e->prof_ids = new std::vector<int>();
+  e->cfg = *cfg;
+  e->device = cfg->device;
+  HsParams& P = e->P;
+  P.n_levels = cfg->levels;
+  P.n_streams = cfg->n_streams;
+  P.max_points = cfg->max_points;
+  P.strict = 0;
+
+  // MapRepMultiMap ctor (HSL/slam_main/MapRepMultiMap.h:48-72): same world offset for every level,
+  // resolution doubles and the grid halves (integer division) per level.
+  float res = cfg->map_resolution;
+  int sx = cfg->map_size_x, sy = cfg->map_size_y;
+  volatile float total_x = res * (float)sx;
+  volatile float mid_x = total_x * cfg->start_x;
+  volatile float total_y = res * (float)sy;
+  volatile float mid_y = total_y * cfg->start_y;
+  unsigned long long off = 0;
+  for (int i = 0; i < cfg->levels; ++i) {
+    HsLevel& L = P.lv[i];
+    L.sx = sx;
+    L.sy = sy;
+    L.limx = (float)sx - 2.0f;
+    L.limy = (float)sy - 2.0f;
+    L.pt_factor = (float)(1.0 / pow(2.0, (double)i));
+    L.max_iter = (i == 0) ? 5 : 3;
+    L.cell_offset = off;
+    level_transform(&L, mid_x, mid_y, res);
+    off += (unsigned long long)sx * (unsigned long long)sy;
+    sx /= 2;
+    sy /= 2;
+    res *= 2.0f;
+  }
+  P.cells_per_stream = off;
+  e->free_factor = 0.4f;
+  e->occ_factor = 0.6f;
+  P.log_odds_free = prob_to_log_odds(0.4f);
+  P.log_odds_occ = prob_to_log_odds(0.6f);
+  P.min_dist = 0.4f * 1.0f;
+  P.min_angle = 0.13f * 1.0f;
+
+  const size_t ns = (size_t)cfg->n_streams, mp = (size_t)cfg->max_points;
+  const size_t cells = ns * (size_t)P.cells_per_stream;
+  int st = HS_OK;
+#define HS_ALLOC(ptr, bytes)                                            \
+  if (st == HS_OK) {                                                    \
+    cudaError_t err__ = cudaMalloc((void**)&(ptr), (bytes));            \
+    if (err__ != cudaSuccess) st = (err__ == cudaErrorMemoryAllocation) ? HS_ERR_OUT_OF_MEMORY : (int)err__; \
+  }
+  HS_ALLOC(P.val, cells * sizeof(float));
+  HS_ALLOC(P.idx, cells * sizeof(int));
+  HS_ALLOC(P.last_pose, ns * 3 * sizeof(float));
+  HS_ALLOC(P.last_update_pose, ns * 3 * sizeof(float));
+  HS_ALLOC(P.cov, ns * 9 * sizeof(float));
+  HS_ALLOC(P.cur_update_index, ns * sizeof(int));
+  HS_ALLOC(P.last_update_index, ns * sizeof(int));
+  HS_ALLOC(P.coarse_pts, ns * mp * 2 * sizeof(float));
+  HS_ALLOC(P.coarse_cnt, ns * sizeof(int));
+  HS_ALLOC(P.coarse_origo, ns * 2 * sizeof(float));
+  HS_ALLOC(P.slot_pose, ns * 3 * sizeof(float));
+  HS_ALLOC(P.slot_integrate, ns * sizeof(int));
+  HS_ALLOC(P.slot_mark_base, ns * sizeof(int));
+  HS_ALLOC(P.counters, 4 * sizeof(unsigned long long));
+  HS_ALLOC(e->d_points, ns * mp * 2 * sizeof(float));
+  HS_ALLOC(e->d_counts, ns * sizeof(int32_t));
+  HS_ALLOC(e->d_origos, ns * 2 * sizeof(float));
+  HS_ALLOC(e->d_hints, ns * 3 * sizeof(float));
+  HS_ALLOC(e->d_flags, ns * sizeof(uint8_t));
+  HS_ALLOC(e->d_ids, ns * sizeof(int32_t));
+  HS_ALLOC(e->d_out, ns * 9 * sizeof(float));
+#undef HS_ALLOC
+  if (st == HS_OK) {
+    cudaError_t err = cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking);
+    if (err != cudaSuccess) st = (int)err;
+  }
+  if (st != HS_OK) {
+    cudaGetLastError();
+    hs_destroy(e);
+    return st;
+  }
+  e->stream = e->own_stream;
+  cudaMemsetAsync(P.counters, 0, 4 * sizeof(unsigned long long), e->stream);
+  cudaMemsetAsync(P.slot_integrate, 0, ns * sizeof(int), e->stream);
+  cudaMemsetAsync(P.coarse_pts, 0, ns * mp * 2 * sizeof(float), e->stream);
+  k_reset_state<<<(cfg->n_streams + 127) / 128, 128, 0, e->stream>>>(P, 0, cfg->n_streams, 1);
+  e->launches++;
+  k_clear_cells<<<148 * 8, 256, 0, e->stream>>>(P.val, P.idx, cells);
+  e->launches++;
+  cudaError_t err = cudaStreamSynchronize(e->stream);
+  if (err != cudaSuccess) {
+    hs_destroy(e);
+    return (int)err;
+  }
+  *out = e;
+  return HS_OK;
+}
+
+int hs_destroy(hs_engine* e) {
+  if (!e) return HS_OK;
+  cudaSetDevice(e->device);
+  if (e->own_stream) cudaStreamSynchronize(e->own_stream);
+  HsParams& P = e->P;
+  void* ptrs[] = {P.val, P.idx, P.last_pose, P.last_update_pose, P.cov, P.cur_update_index, P.last_update_index,
+                  P.coarse_pts, P.coarse_cnt, P.coarse_origo, P.slot_pose, P.slot_integrate, P.slot_mark_base, P.counters,
+                  e->d_points, e->d_counts, e->d_origos, e->d_hints, e->d_flags, e->d_ids, e->d_ranges, e->d_out,
+                  e->d_beam_cs, e->d_scratch};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  if (e->own_stream) cudaStreamDestroy(e->own_stream);
+  if (e->prof_events) {
+    for (cudaEvent_t ev : *e->prof_events) cudaEventDestroy(ev);
+    delete e->prof_events;
+    delete e->prof_ids;
+  }
+  delete e;
+  return HS_OK;
+}
+
+int hs_reset(hs_engine* e, int stream) {
+  if (!e) return HS_ERR_INVALID_ARG;
+  if (stream != HS_ALL_STREAMS && (stream < 0 || stream >= e->P.n_streams)) return HS_ERR_INVALID_ARG;
+  HS_CK(cudaSetDevice(e->device));
+  int first = stream == HS_ALL_STREAMS ? 0 : stream;
+  int n = stream == HS_ALL_STREAMS ? e->P.n_streams : 1;
+  k_reset_state<<<(n + 127) / 128, 128, 0, e->stream>>>(e->P, first, n, 0);
+  HS_LAUNCHED(e);
+  size_t cells = (size_t)n * (size_t)e->P.cells_per_stream;
+  size_t base = (size_t)first * (size_t)e->P.cells_per_stream;
+  k_clear_cells<<<148 * 8, 256, 0, e->stream>>>(e->P.val + base, e->P.idx + base, cells);
+  HS_LAUNCHED(e);
+  return HS_OK;
+}
+
+int hs_set_update_factor_free(hs_engine* e, float f) {
+  if (!e) return HS_ERR_INVALID_ARG;
+  e->free_factor = f;
+  e->P.log_odds_free = prob_to_log_odds(f);
+  return HS_OK;
+}
+int hs_set_update_factor_occupied(hs_engine* e, float f) {
+  if (!e) return HS_ERR_INVALID_ARG;
+  e->occ_factor = f;
+  e->P.log_odds_occ = prob_to_log_odds(f);
+  return HS_OK;
+}
+int hs_set_map_update_min_dist_diff(hs_engine* e, float d) {
+  if (!e) return HS_ERR_INVALID_ARG;
+  e->P.min_dist = d;
+  return HS_OK;
+}
+int hs_set_map_update_min_angle_diff(hs_engine* e, float a) {
+  if (!e) return HS_ERR_INVALID_ARG;
+  e->P.min_angle = a;
+  return HS_OK;
+}
+int hs_set_strict_summation(hs_engine* e, int on) {
+  if (!e) return HS_ERR_INVALID_ARG;
+  e->P.strict = on ? 1 : 0;
+  return HS_OK;
+}
+float hs_get_scale_to_map(const hs_engine* e) { return e ? e->P.lv[0].scale : 0.0f; }
+int hs_get_map_levels(const hs_engine* e) { return e ? e->P.n_levels : 0; }
+int hs_get_n_streams(const hs_engine* e) { return e ? e->P.n_streams : 0; }
+int hs_get_max_points(const hs_engine* e) { return e ? e->P.max_points : 0; }
+int hs_get_level_dims(const hs_engine* e, int level, int* sx, int* sy, float* cell_length) {
+  if (!e || level < 0 || level >= e->P.n_levels) return HS_ERR_INVALID_ARG;
+  if (sx) *sx = e->P.lv[level].sx;
+  if (sy) *sy = e->P.lv[level].sy;
+  if (cell_length) {
+    float res = e->cfg.map_resolution;
+    for (int i = 0; i < level; ++i) res *= 2.0f;
+    *cell_length = res;
+  }
+  return HS_OK;
+}
+int hs_set_cuda_stream(hs_engine* e, void* cuda_stream) {
+  if (!e) return HS_ERR_INVALID_ARG;
+  HS_CK(cudaSetDevice(e->device));
+  HS_CK(cudaStreamSynchronize(e->stream));
+  e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
+  return HS_OK;
+}
+int hs_synchronize(hs_engine* e) {
+  if (!e) return HS_ERR_INVALID_ARG;
+  HS_CK(cudaSetDevice(e->device));
+  HS_CK(cudaStreamSynchronize(e->stream));
+  return HS_OK;
+}
+
+// ---- the hot path ----------------------------------------------------------------------------
+
+static int check_batch(const hs_engine* e, int n) {
+  if (!e) return HS_ERR_INVALID_ARG;
+  if (n < 0 || n > e->P.n_streams) return HS_ERR_INVALID_ARG;
+  return HS_OK;
+}
+
+// match (+gate) then ray-cast, all pointers on the device
+static int run_update_device(hs_engine* e, int n, const int32_t* ids, const float* points, const int32_t* counts,
+                             const float* origos, const float* hints, const uint8_t* flags, int mode) {
+  if (n == 0) return HS_OK;
+  const int threads = 128;
+  {
+    ProfScope ps(e, HS_K_MATCH);
+    if (e->P.strict)
+      k_match<true><<<warp_grid(n, threads), threads, 0, e->stream>>>(e->P, n, ids, (const float2*)points, counts,
+                                                                      (const float2*)origos, hints, flags, mode);
+    else
+      k_match<false><<<warp_grid(n, threads), threads, 0, e->stream>>>(e->P, n, ids, (const float2*)points, counts,
+                                                                       (const float2*)origos, hints, flags, mode);
+  }
+  HS_LAUNCHED(e);
+  if (mode == 0) {
+    {
+      ProfScope ps(e, HS_K_RAYCAST);
+      k_raycast<<<n * e->P.n_levels, 256, 0, e->stream>>>(e->P, n, ids, (const float2*)points, counts, (const float2*)origos);
+    }
+    HS_LAUNCHED(e);
+  }
+  e->updates += (uint64_t)n;
+  return HS_OK;
+}
+
+__global__ void k_gather_rows(const float* __restrict__ src, const int32_t* __restrict__ ids, int n, int width, float* __restrict__ dst) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * width) return;
+  int r = i / width, c = i - r * width;
+  dst[i] = src[(size_t)ids[r] * width + c];
+}
+
+static int fetch_rows(hs_engine* e, const float* d_src, const int32_t* d_ids, int first, int n, int width, float* host_out) {
+  if (!host_out || n == 0) return HS_OK;
+  size_t bytes = (size_t)n * width * sizeof(float);
+  if (d_ids) {
+    k_gather_rows<<<(n * width + 255) / 256, 256, 0, e->stream>>>(d_src, d_ids, n, width, e->d_out);
+    HS_LAUNCHED(e);
+    HS_CK(cudaMemcpyAsync(host_out, e->d_out, bytes, cudaMemcpyDeviceToHost, e->stream));
+  } else {
+    HS_CK(cudaMemcpyAsync(host_out, d_src + (size_t)first * width, bytes, cudaMemcpyDeviceToHost, e->stream));
+  }
+  e->d2h_bytes += bytes;
+  return HS_OK;
+}
+
+static int stage_common(hs_engine* e, int n, const int32_t* ids, const int32_t* counts, const float* origos,
+                        const float* hints, const uint8_t* flags) {
+  if (ids) { HS_CK(cudaMemcpyAsync(e->d_ids, ids, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream)); e->h2d_bytes += (size_t)n * 4; }
+  if (counts) { HS_CK(cudaMemcpyAsync(e->d_counts, counts, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream)); e->h2d_bytes += (size_t)n * 4; }
+  if (origos) { HS_CK(cudaMemcpyAsync(e->d_origos, origos, (size_t)n * 2 * sizeof(float), cudaMemcpyHostToDevice, e->stream)); e->h2d_bytes += (size_t)n * 8; }
+  if (hints) { HS_CK(cudaMemcpyAsync(e->d_hints, hints, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, e->stream)); e->h2d_bytes += (size_t)n * 12; }
+  if (flags) { HS_CK(cudaMemcpyAsync(e->d_flags, flags, (size_t)n, cudaMemcpyHostToDevice, e->stream)); e->h2d_bytes += (size_t)n; }
+  return HS_OK;
+}
+
+static int check_ids(const hs_engine* e, int n, const int32_t* ids) {
+  if (!ids) return HS_OK;
+  for (int i = 0; i < n; ++i)
+    if (ids[i] < 0 || ids[i] >= e->P.n_streams) return HS_ERR_INVALID_ARG;
+  return HS_OK;
+}
+
+int hs_update_batch_device(hs_engine* e, int n, const int32_t* stream_ids, const float* points, const int32_t* counts,
+                           const float* origos, const float* pose_hints, const uint8_t* map_without_matching) {
+  int st = check_batch(e, n);
+  if (st != HS_OK) return st;
+  if (n > 0 && (!points || !counts)) return HS_ERR_INVALID_ARG;
+  HS_CK(cudaSetDevice(e->device));
+  return run_update_device(e, n, stream_ids, points, counts, origos, pose_hints, map_without_matching, 0);
+}
+
+static int update_host(hs_engine* e, int n, const int32_t* ids, const float* points, const int32_t* counts, const float* origos,
+                       const float* hints, const uint8_t* flags, float* poses_out, float* cov_out, int mode) {
+  int st = check_batch(e, n);
+  if (st != HS_OK) return st;
+  if (n == 0) return HS_OK;
+  if (!points || !counts) return HS_ERR_INVALID_ARG;
+  if ((st = check_ids(e, n, ids)) != HS_OK) return st;
+  HS_CK(cudaSetDevice(e->device));
+  size_t pbytes = (size_t)n * e->P.max_points * 2 * sizeof(float);
+  HS_CK(cudaMemcpyAsync(e->d_points, points, pbytes, cudaMemcpyHostToDevice, e->stream));
+  e->h2d_bytes += pbytes;
+  if ((st = stage_common(e, n, ids, counts, origos, hints, flags)) != HS_OK) return st;
+  st = run_update_device(e, n, ids ? e->d_ids : nullptr, e->d_points, e->d_counts, origos ? e->d_origos : nullptr,
+                         hints ? e->d_hints : nullptr, flags ? e->d_flags : nullptr, mode);
+  if (st != HS_OK) return st;
+  if ((st = fetch_rows(e, e->P.last_pose, ids ? e->d_ids : nullptr, 0, n, 3, poses_out)) != HS_OK) return st;
+  if (cov_out) {
+    if (ids && poses_out) HS_CK(cudaStreamSynchronize(e->stream));  // d_out is reused by the second gather
+    if ((st = fetch_rows(e, e->P.cov, ids ? e->d_ids : nullptr, 0, n, 9, cov_out)) != HS_OK) return st;
+  }
+  HS_CK(cudaStreamSynchronize(e->stream));
+  return HS_OK;
+}
+
+int hs_update_batch(hs_engine* e, int n, const int32_t* stream_ids, const float* points, const int32_t* counts,
+                    const float* origos, const float* pose_hints, const uint8_t* map_without_matching,
+                    float* poses_out, float* cov_out) {
+  return update_host(e, n, stream_ids, points, counts, origos, pose_hints, map_without_matching, poses_out, cov_out, 0);
+}
+
+int hs_match_batch(hs_engine* e, int n, const int32_t* stream_ids, const float* points, const int32_t* counts,
+                   const float* origos, const float* pose_hints, float* poses_out, float* cov_out) {
+  return update_host(e, n, stream_ids, points, counts, origos, pose_hints, nullptr, poses_out, cov_out, 1);
+}
+
+int hs_set_scan_geometry(hs_engine* e, int n_beams, float angle_min, float angle_increment, float range_min, float range_max) {
+  if (!e || n_beams < 1 || n_beams > e->P.max_points) return HS_ERR_INVALID_ARG;
+  HS_CK(cudaSetDevice(e->device));
+  HS_CK(cudaStreamSynchronize(e->stream));
+  if (e->d_beam_cs) { cudaFree(e->d_beam_cs); e->d_beam_cs = nullptr; }
+  if (e->d_ranges) { cudaFree(e->d_ranges); e->d_ranges = nullptr; }
+  // rosLaserScanToDataContainer (HectorMappingRos.cpp:487, :505): float accumulation of the beam angle;
+  // cos/sin from the host libm, as the reference's caller computes them.
+  std::vector<float2> cs((size_t)n_beams);
+  volatile float angle = angle_min;
+  for (int i = 0; i < n_beams; ++i) {
+    float a = angle;
+    cs[i] = make_float2(cosf(a), sinf(a));
+    angle = angle + angle_increment;
+  }
+  HS_CK(cudaMalloc((void**)&e->d_beam_cs, (size_t)n_beams * sizeof(float2)));
+  HS_CK(cudaMalloc((void**)&e->d_ranges, (size_t)e->P.n_streams * n_beams * sizeof(float)));
+  HS_CK(cudaMemcpy(e->d_beam_cs, cs.data(), (size_t)n_beams * sizeof(float2), cudaMemcpyHostToDevice));
+  e->n_beams = n_beams;
+  e->angle_min = angle_min;
+  e->angle_increment = angle_increment;
+  e->range_min = range_min;
+  e->range_max = range_max;
+  volatile float mr = range_max - 0.1f;
+  e->max_range_for_container = mr;
+  return HS_OK;
+}
+
+int hs_update_batch_ranges_device(hs_engine* e, int n, const int32_t* stream_ids, const float* ranges,
+                                  const float* pose_hints, const uint8_t* map_without_matching) {
+  int st = check_batch(e, n);
+  if (st != HS_OK) return st;
+  if (!e->d_beam_cs) return HS_ERR_NOT_CONFIGURED;
+  if (n == 0) return HS_OK;
+  if (!ranges) return HS_ERR_INVALID_ARG;
+  HS_CK(cudaSetDevice(e->device));
+  const int threads = 128;
+  {
+    ProfScope ps(e, HS_K_SCAN_TO_POINTS);
+    k_scan_to_points<<<warp_grid(n, threads), threads, 0, e->stream>>>(ranges, n, e->n_beams, e->d_beam_cs, e->range_min,
+                                                                       e->max_range_for_container, e->P.lv[0].scale,
+                                                                       e->P.max_points, (float2*)e->d_points, e->d_counts);
+  }
+  HS_LAUNCHED(e);
+  return run_update_device(e, n, stream_ids, e->d_points, e->d_counts, nullptr, pose_hints, map_without_matching, 0);
+}
+
+int hs_update_batch_ranges(hs_engine* e, int n, const int32_t* stream_ids, const float* ranges, const float* pose_hints,
+                           const uint8_t* map_without_matching, float* poses_out, float* cov_out) {
+  int st = check_batch(e, n);
+  if (st != HS_OK) return st;
+  if (!e->d_beam_cs) return HS_ERR_NOT_CONFIGURED;
+  if (n == 0) return HS_OK;
+  if (!ranges) return HS_ERR_INVALID_ARG;
+  if ((st = check_ids(e, n, stream_ids)) != HS_OK) return st;
+  HS_CK(cudaSetDevice(e->device));
+  size_t rbytes = (size_t)n * e->n_beams * sizeof(float);
+  HS_CK(cudaMemcpyAsync(e->d_ranges, ranges, rbytes, cudaMemcpyHostToDevice, e->stream));
+  e->h2d_bytes += rbytes;
+  if ((st = stage_common(e, n, stream_ids, nullptr, nullptr, pose_hints, map_without_matching)) != HS_OK) return st;
+  st = hs_update_batch_ranges_device(e, n, stream_ids ? e->d_ids : nullptr, e->d_ranges, pose_hints ? e->d_hints : nullptr,
+                                     map_without_matching ? e->d_flags : nullptr);
+  if (st != HS_OK) return st;
+  if ((st = fetch_rows(e, e->P.last_pose, stream_ids ? e->d_ids : nullptr, 0, n, 3, poses_out)) != HS_OK) return st;
+  if (cov_out) {
+    if (stream_ids && poses_out) HS_CK(cudaStreamSynchronize(e->stream));
+    if ((st = fetch_rows(e, e->P.cov, stream_ids ? e->d_ids : nullptr, 0, n, 9, cov_out)) != HS_OK) return st;
+  }
+  HS_CK(cudaStreamSynchronize(e->stream));
+  return HS_OK;
+}
+
+static int get_rows(hs_engine* e, const float* d_src, int first, int n, int width, float* out) {
+  if (!e || !out || first < 0 || n < 0 || first + n > e->P.n_streams) return HS_ERR_INVALID_ARG;
+  HS_CK(cudaSetDevice(e->device));
+  int st = fetch_rows(e, d_src, nullptr, first, n, width, out);
+  if (st != HS_OK) return st;
+  HS_CK(cudaStreamSynchronize(e->stream));
+  return HS_OK;
+}
+int hs_get_poses(hs_engine* e, int first, int n, float* poses_out) { return get_rows(e, e ? e->P.last_pose : nullptr, first, n, 3, poses_out); }
+int hs_get_covariances(hs_engine* e, int first, int n, float* cov_out) { return get_rows(e, e ? e->P.cov : nullptr, first, n, 9, cov_out); }
+int hs_get_last_map_update_poses(hs_engine* e, int first, int n, float* poses_out) {
+  return get_rows(e, e ? e->P.last_update_pose : nullptr, first, n, 3, poses_out);
+}
+const float* hs_device_pose_ptr(const hs_engine* e) { return e ? e->P.last_pose : nullptr; }
+
+// ---- single-function entry points --------------------------------------------------------------
+
+int hs_hessian_derivs_batch(hs_engine* e, int stream, int level, const float* poses_map, int n_poses, const float* points,
+                            int n_points, float* H9, float* dTr3) {
+  if (!e || stream < 0 || stream >= e->P.n_streams || level < 0 || level >= e->P.n_levels || n_poses < 0 || n_points < 0)
+    return HS_ERR_INVALID_ARG;
+  if (n_poses == 0) return HS_OK;
+  if (!poses_map || (!points && n_points > 0) || !H9 || !dTr3) return HS_ERR_INVALID_ARG;
+  HS_CK(cudaSetDevice(e->device));
+  size_t b_poses = (size_t)n_poses * 3 * sizeof(float), b_pts = (size_t)(n_points > 0 ? n_points : 1) * 2 * sizeof(float);
+  size_t b_h = (size_t)n_poses * 9 * sizeof(float), b_d = (size_t)n_poses * 3 * sizeof(float);
+  auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  size_t o_pts = align(b_poses), o_h = o_pts + align(b_pts), o_d = o_h + align(b_h), total = o_d + align(b_d);
+  int st = ensure_scratch(e, total);
+  if (st != HS_OK) return st;
+  char* base = (char*)e->d_scratch;
+  HS_CK(cudaMemcpyAsync(base, poses_map, b_poses, cudaMemcpyHostToDevice, e->stream));
+  if (n_points > 0) HS_CK(cudaMemcpyAsync(base + o_pts, points, (size_t)n_points * 2 * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  e->h2d_bytes += b_poses + (size_t)n_points * 8;
+  const int threads = 128;
+  if (e->P.strict)
+    k_hessian_derivs<true><<<warp_grid(n_poses, threads), threads, 0, e->stream>>>(
+        e->P, stream, level, (const float*)base, n_poses, (const float2*)(base + o_pts), n_points, (float*)(base + o_h), (float*)(base + o_d));
+  else
+    k_hessian_derivs<false><<<warp_grid(n_poses, threads), threads, 0, e->stream>>>(
+        e->P, stream, level, (const float*)base, n_poses, (const float2*)(base + o_pts), n_points, (float*)(base + o_h), (float*)(base + o_d));
+  HS_LAUNCHED(e);
+  HS_CK(cudaMemcpyAsync(H9, base + o_h, b_h, cudaMemcpyDeviceToHost, e->stream));
+  HS_CK(cudaMemcpyAsync(dTr3, base + o_d, b_d, cudaMemcpyDeviceToHost, e->stream));
+  e->d2h_bytes += b_h + b_d;
+  HS_CK(cudaStreamSynchronize(e->stream));
+  return HS_OK;
+}
+
+int hs_raycast_batch(hs_engine* e, int n, const int32_t* stream_ids, const float* points, const int32_t* counts,
+                     const float* origos, const float* poses_world) {
+  int st = check_batch(e, n);
+  if (st != HS_OK) return st;
+  if (n == 0) return HS_OK;
+  if (!points || !counts || !poses_world) return HS_ERR_INVALID_ARG;
+  if ((st = check_ids(e, n, stream_ids)) != HS_OK) return st;
+  HS_CK(cudaSetDevice(e->device));
+  size_t pbytes = (size_t)n * e->P.max_points * 2 * sizeof(float);
+  HS_CK(cudaMemcpyAsync(e->d_points, points, pbytes, cudaMemcpyHostToDevice, e->stream));
+  e->h2d_bytes += pbytes;
+  if ((st = stage_common(e, n, stream_ids, counts, origos, poses_world, nullptr)) != HS_OK) return st;
+  const int32_t* d_ids = stream_ids ? e->d_ids : nullptr;
+  const float2* d_or = origos ? (const float2*)e->d_origos : nullptr;
+  const int threads = 128;
+  k_force_integrate<<<warp_grid(n, threads), threads, 0, e->stream>>>(e->P, n, d_ids, (const float2*)e->d_points, e->d_counts, d_or, e->d_hints);
+  HS_LAUNCHED(e);
+  k_raycast<<<n * e->P.n_levels, 256, 0, e->stream>>>(e->P, n, d_ids, (const float2*)e->d_points, e->d_counts, d_or);
+  HS_LAUNCHED(e);
+  HS_CK(cudaStreamSynchronize(e->stream));
+  return HS_OK;
+}
+
+// ---- map access ----------------------------------------------------------------------------------
+
+static int check_level(const hs_engine* e, int stream, int level) {
+  if (!e || stream < 0 || stream >= e->P.n_streams || level < 0 || level >= e->P.n_levels) return HS_ERR_INVALID_ARG;
+  return HS_OK;
+}
+
+int hs_download_level(hs_engine* e, int stream, int level, hs_cell* cells_out) {
+  int st = check_level(e, stream, level);
+  if (st != HS_OK) return st;
+  if (!cells_out) return HS_ERR_INVALID_ARG;
+  HS_CK(cudaSetDevice(e->device));
+  const HsLevel& L = e->P.lv[level];
+  size_t n = (size_t)L.sx * L.sy;
+  if ((st = ensure_scratch(e, n * sizeof(hs_cell))) != HS_OK) return st;
+  size_t base = (size_t)stream * (size_t)e->P.cells_per_stream + (size_t)L.cell_offset;
+  k_pack_cells<<<148 * 4, 256, 0, e->stream>>>(e->P.val + base, e->P.idx + base, (hs_cell*)e->d_scratch, n);
+  HS_LAUNCHED(e);
+  HS_CK(cudaMemcpyAsync(cells_out, e->d_scratch, n * sizeof(hs_cell), cudaMemcpyDeviceToHost, e->stream));
+  e->d2h_bytes += n * sizeof(hs_cell);
+  HS_CK(cudaStreamSynchronize(e->stream));
+  return HS_OK;
+}
+
+int hs_upload_level(hs_engine* e, int stream, int level, const hs_cell* cells_in) {
+  int st = check_level(e, stream, level);
+  if (st != HS_OK) return st;
+  if (!cells_in) return HS_ERR_INVALID_ARG;
+  HS_CK(cudaSetDevice(e->device));
+  const HsLevel& L = e->P.lv[level];
+  size_t n = (size_t)L.sx * L.sy;
+  if ((st = ensure_scratch(e, n * sizeof(hs_cell))) != HS_OK) return st;
+  size_t base = (size_t)stream * (size_t)e->P.cells_per_stream + (size_t)L.cell_offset;
+  HS_CK(cudaMemcpyAsync(e->d_scratch, cells_in, n * sizeof(hs_cell), cudaMemcpyHostToDevice, e->stream));
+  e->h2d_bytes += n * sizeof(hs_cell);
+  k_unpack_cells<<<148 * 4, 256, 0, e->stream>>>((const hs_cell*)e->d_scratch, e->P.val + base, e->P.idx + base, n);
+  HS_LAUNCHED(e);
+  HS_CK(cudaStreamSynchronize(e->stream));
+  return HS_OK;
+}
+
+int hs_get_update_index(hs_engine* e, int stream, int level, int* update_index_out) {
+  int st = check_level(e, stream, level);
+  if (st != HS_OK) return st;
+  if (!update_index_out) return HS_ERR_INVALID_ARG;
+  HS_CK(cudaSetDevice(e->device));
+  HS_CK(cudaMemcpyAsync(update_index_out, e->P.last_update_index + stream, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  HS_CK(cudaStreamSynchronize(e->stream));
+  return HS_OK;
+}
+
+int hs_classify_level(hs_engine* e, int stream, int level, int8_t* occupancy_out) {
+  int st = check_level(e, stream, level);
+  if (st != HS_OK) return st;
+  if (!occupancy_out) return HS_ERR_INVALID_ARG;
+  HS_CK(cudaSetDevice(e->device));
+  const HsLevel& L = e->P.lv[level];
+  size_t n = (size_t)L.sx * L.sy;
+  if ((st = ensure_scratch(e, n)) != HS_OK) return st;
+  size_t base = (size_t)stream * (size_t)e->P.cells_per_stream + (size_t)L.cell_offset;
+  k_classify<<<148 * 4, 256, 0, e->stream>>>(e->P.val + base, (int8_t*)e->d_scratch, n);
+  HS_LAUNCHED(e);
+  HS_CK(cudaMemcpyAsync(occupancy_out, e->d_scratch, n, cudaMemcpyDeviceToHost, e->stream));
+  e->d2h_bytes += n;
+  HS_CK(cudaStreamSynchronize(e->stream));
+  return HS_OK;
+}
+
+int hs_get_stats(hs_engine* e, hs_stats* out) {
+  if (!e || !out) return HS_ERR_INVALID_ARG;
+  HS_CK(cudaSetDevice(e->device));
+  unsigned long long c[4];
+  HS_CK(cudaMemcpyAsync(c, e->P.counters, sizeof(c), cudaMemcpyDeviceToHost, e->stream));
+  HS_CK(cudaStreamSynchronize(e->stream));
+  out->updates = e->updates;
+  out->integrations = c[1];
+  out->angle_clamps = c[2];
+  out->cell_visits = c[3];
+  out->kernel_launches = e->launches;
+  out->h2d_bytes = e->h2d_bytes;
+  out->d2h_bytes = e->d2h_bytes;
+  return HS_OK;
+}
+
+int hs_profile_enable(hs_engine* e, int on) {
+  if (!e) return HS_ERR_INVALID_ARG;
+  HS_CK(cudaSetDevice(e->device));
+  HS_CK(cudaStreamSynchronize(e->stream));
+  e->profiling = on ? 1 : 0;
+  e->prof_used = 0;
+  e->prof_ids->clear();
+  return HS_OK;
+}
+
+int hs_profile_collect(hs_engine* e, hs_kernel_times* out) {
+  if (!e || !out) return HS_ERR_INVALID_ARG;
+  HS_CK(cudaSetDevice(e->device));
+  HS_CK(cudaStreamSynchronize(e->stream));
+  memset(out, 0, sizeof(*out));
+  for (size_t i = 0; i < e->prof_ids->size(); ++i) {
+    float ms = 0.0f;
+    HS_CK(cudaEventElapsedTime(&ms, (*e->prof_events)[2 * i], (*e->prof_events)[2 * i + 1]));
+    int id = (*e->prof_ids)[i];
+    if (id >= 0 && id < HS_K_COUNT) {
+      out->ms[id] += (double)ms;
+      out->launches[id] += 1;
+    }
+  }
+  e->prof_used = 0;
+  e->prof_ids->clear();
+  return HS_OK;
+}
+
+}  // extern "C"

@@ -10,6 +10,7 @@
  * Also holds hs_scan_to_points_host, the host twin of the k_scan_to_points kernel: the arithmetic of
  * HectorMappingRos::rosLaserScanToDataContainer (src/hector_slam/hector_mapping/src/HectorMappingRos.cpp:483-507).
  */
+#define _GNU_SOURCE
 #include "hsgpu.h"
 
 #include <math.h>
