@@ -7,7 +7,7 @@ strict-summation mode must reproduce the oracle bit for bit in closed loop.
 import numpy as np
 import pytest
 
-from conftest import bits, make_streams
+from hs_testutil import bits, make_streams
 
 pytestmark = pytest.mark.gpu
 

@@ -87,6 +87,15 @@ static inline int hs_launch_check(hs_engine* e) {
     if (st__ != HS_OK) return st__;    \
   } while (0)
 
+static int raycast_log2_hash(int max_points) {
+  int l = 4;
+  while ((1 << l) < 2 * max_points) ++l;
+  return l;
+}
+static size_t raycast_smem_for(int max_points) {
+  return (size_t)HS_MAP_BYTES + 2 * sizeof(int) * ((size_t)1 << raycast_log2_hash(max_points)) + (size_t)max_points * sizeof(HsBeamRec);
+}
+static size_t raycast_smem(const hs_engine* e) { return raycast_smem_for(e->P.max_points); }
 static int warp_grid(int n_warps, int threads) { return (n_warps * 32 + threads - 1) / threads; }
 
 // GridMapLogOddsFunctions::probToLogOdds (HSL/map/GridMapLogOdds.h:198-203), host libm like the reference.
@@ -144,7 +153,7 @@ const char* hs_status_string(int status) {
 int hs_create(const hs_config* cfg, hs_engine** out) {
   if (!cfg || !out) return HS_ERR_INVALID_ARG;
   *out = nullptr;
-  if (cfg->levels < 1 || cfg->levels > HS_MAX_LEVELS || cfg->n_streams < 1 || cfg->max_points < 1 ||
+  if (cfg->levels < 1 || cfg->levels > HS_MAX_LEVELS || cfg->n_streams < 1 || cfg->max_points < 1 || cfg->max_points > 5600 ||
       cfg->map_size_x < 2 || cfg->map_size_y < 2 || !(cfg->map_resolution > 0.0f))
     return HS_ERR_INVALID_ARG;
   if ((cfg->map_size_x >> (cfg->levels - 1)) < 2 || (cfg->map_size_y >> (cfg->levels - 1)) < 2) return HS_ERR_INVALID_ARG;
@@ -165,7 +174,7 @@ int hs_create(const hs_config* cfg, hs_engine** out) {
   P.n_levels = cfg->levels;
   P.n_streams = cfg->n_streams;
   P.max_points = cfg->max_points;
-  P.strict = 0;
+  P.strict = 1;  // reference-order sums by default: bitwise the CPU reference's poses
 
   // MapRepMultiMap ctor (HSL/slam_main/MapRepMultiMap.h:48-72): same world offset for every level,
   // resolution doubles and the grid halves (integer division) per level.
@@ -239,6 +248,25 @@ int hs_create(const hs_config* cfg, hs_engine** out) {
     return st;
   }
   e->stream = e->own_stream;
+  {
+    int smem = cfg->max_points * HS_NPROD * (int)sizeof(float);  // k_match's per-CTA product buffer
+    if (smem > 48 * 1024) {
+      cudaError_t e1 = cudaFuncSetAttribute(k_match<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      cudaError_t e2 = cudaFuncSetAttribute(k_match<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e1 != cudaSuccess || e2 != cudaSuccess) {
+        hs_destroy(e);
+        return (int)(e1 != cudaSuccess ? e1 : e2);
+      }
+    }
+    int smem_r = (int)raycast_smem_for(cfg->max_points);  // k_raycast's cell map + hash table + beam records
+    if (smem_r > 48 * 1024) {
+      cudaError_t e3 = cudaFuncSetAttribute(k_raycast, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_r);
+      if (e3 != cudaSuccess) {
+        hs_destroy(e);
+        return (int)e3;
+      }
+    }
+  }
   cudaMemsetAsync(P.counters, 0, 4 * sizeof(unsigned long long), e->stream);
   cudaMemsetAsync(P.slot_integrate, 0, ns * sizeof(int), e->stream);
   cudaMemsetAsync(P.coarse_pts, 0, ns * mp * 2 * sizeof(float), e->stream);
@@ -359,21 +387,22 @@ static int check_batch(const hs_engine* e, int n) {
 static int run_update_device(hs_engine* e, int n, const int32_t* ids, const float* points, const int32_t* counts,
                              const float* origos, const float* hints, const uint8_t* flags, int mode) {
   if (n == 0) return HS_OK;
-  const int threads = 128;
+  const size_t smem = (size_t)e->P.max_points * HS_NPROD * sizeof(float);
   {
     ProfScope ps(e, HS_K_MATCH);
     if (e->P.strict)
-      k_match<true><<<warp_grid(n, threads), threads, 0, e->stream>>>(e->P, n, ids, (const float2*)points, counts,
-                                                                      (const float2*)origos, hints, flags, mode);
+      k_match<true><<<n, HS_MATCH_THREADS, smem, e->stream>>>(e->P, n, ids, (const float2*)points, counts,
+                                                             (const float2*)origos, hints, flags, mode);
     else
-      k_match<false><<<warp_grid(n, threads), threads, 0, e->stream>>>(e->P, n, ids, (const float2*)points, counts,
-                                                                       (const float2*)origos, hints, flags, mode);
+      k_match<false><<<n, HS_MATCH_THREADS, smem, e->stream>>>(e->P, n, ids, (const float2*)points, counts,
+                                                              (const float2*)origos, hints, flags, mode);
   }
   HS_LAUNCHED(e);
   if (mode == 0) {
     {
       ProfScope ps(e, HS_K_RAYCAST);
-      k_raycast<<<n * e->P.n_levels, 256, 0, e->stream>>>(e->P, n, ids, (const float2*)points, counts, (const float2*)origos);
+      k_raycast<<<n * e->P.n_levels, HS_RAYCAST_THREADS, raycast_smem(e), e->stream>>>(
+          e->P, n, ids, (const float2*)points, counts, (const float2*)origos, raycast_log2_hash(e->P.max_points));
     }
     HS_LAUNCHED(e);
   }
@@ -569,12 +598,17 @@ int hs_hessian_derivs_batch(hs_engine* e, int stream, int level, const float* po
   HS_CK(cudaMemcpyAsync(base, poses_map, b_poses, cudaMemcpyHostToDevice, e->stream));
   if (n_points > 0) HS_CK(cudaMemcpyAsync(base + o_pts, points, (size_t)n_points * 2 * sizeof(float), cudaMemcpyHostToDevice, e->stream));
   e->h2d_bytes += b_poses + (size_t)n_points * 8;
-  const int threads = 128;
+  const size_t smem = (size_t)(n_points > 0 ? n_points : 1) * HS_NPROD * sizeof(float);
+  if (smem > 200 * 1024) return HS_ERR_INVALID_ARG;
+  if (smem > 48 * 1024) {
+    HS_CK(cudaFuncSetAttribute(k_hessian_derivs<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HS_CK(cudaFuncSetAttribute(k_hessian_derivs<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
   if (e->P.strict)
-    k_hessian_derivs<true><<<warp_grid(n_poses, threads), threads, 0, e->stream>>>(
+    k_hessian_derivs<true><<<n_poses, HS_MATCH_THREADS, smem, e->stream>>>(
         e->P, stream, level, (const float*)base, n_poses, (const float2*)(base + o_pts), n_points, (float*)(base + o_h), (float*)(base + o_d));
   else
-    k_hessian_derivs<false><<<warp_grid(n_poses, threads), threads, 0, e->stream>>>(
+    k_hessian_derivs<false><<<n_poses, HS_MATCH_THREADS, smem, e->stream>>>(
         e->P, stream, level, (const float*)base, n_poses, (const float2*)(base + o_pts), n_points, (float*)(base + o_h), (float*)(base + o_d));
   HS_LAUNCHED(e);
   HS_CK(cudaMemcpyAsync(H9, base + o_h, b_h, cudaMemcpyDeviceToHost, e->stream));
@@ -601,7 +635,8 @@ int hs_raycast_batch(hs_engine* e, int n, const int32_t* stream_ids, const float
   const int threads = 128;
   k_force_integrate<<<warp_grid(n, threads), threads, 0, e->stream>>>(e->P, n, d_ids, (const float2*)e->d_points, e->d_counts, d_or, e->d_hints);
   HS_LAUNCHED(e);
-  k_raycast<<<n * e->P.n_levels, 256, 0, e->stream>>>(e->P, n, d_ids, (const float2*)e->d_points, e->d_counts, d_or);
+  k_raycast<<<n * e->P.n_levels, HS_RAYCAST_THREADS, raycast_smem(e), e->stream>>>(
+      e->P, n, d_ids, (const float2*)e->d_points, e->d_counts, d_or, raycast_log2_hash(e->P.max_points));
   HS_LAUNCHED(e);
   HS_CK(cudaStreamSynchronize(e->stream));
   return HS_OK;

@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <float.h>
+#include <limits.h>
 
 #include "hs_libm_exact.h"
 #include "hsgpu.h"
@@ -181,49 +182,76 @@ __device__ __forceinline__ void hs_acc_add(HsAcc& a, float gx, float gy, float r
   a.h12 += gy * rot;
 }
 
-// One evaluation for one warp: all lanes return identical sums.
-//   STRICT = false: each lane accumulates its points (i = lane, lane+32, ...), then a xor-butterfly.
-//   STRICT = true : terms are computed in parallel but added in the reference's order i = 0..n-1
-//                   (every lane walks the 32 shuffled terms of each round), giving bitwise the CPU sums.
+// One evaluation of getCompleteHessianDerivs by a whole CTA. The per-point work (transform, 4 gathers,
+// probabilities, the 9 products) is spread over all threads; the products go to shared memory as
+// prod[i][9] (stride 9 words: conflict-free for both the per-point writes and the per-sum reads).
+// Warp 0 then forms the nine sums and returns them in all of its lanes:
+//   STRICT = true  (default): lanes 0..8 each own one sum and add the n products in the reference's order
+//                   i = 0..n-1 (OccGridMapUtil.h:76-98) -- one dependent FADD chain per sum, bitwise the
+//                   CPU result. fp32 addition is not associative and hector's Gauss-Newton amplifies
+//                   last-bit differences of H/dTr to >1e-4 m on some streams, so this is the mode that
+//                   meets the pose-parity bar.
+//   STRICT = false: every lane sums the points i = lane (mod 32) and a xor-butterfly combines them.
+// Must be called by all threads of the CTA; contains two __syncthreads. Only warp 0's return value is defined.
+#define HS_NPROD 9
+
 template <bool STRICT>
-__device__ __forceinline__ HsAcc hs_eval_warp(const float* __restrict__ val, const HsLevel& L, float ex, float ey, float eth,
-                                              const float2* __restrict__ pts, int n, float pt_factor, int lane) {
-  float sn = hs_sinf(eth), cs = hs_cosf(eth);
+__device__ __forceinline__ HsAcc hs_eval_cta(const float* __restrict__ val, const HsLevel& L, float ex, float ey, float sn, float cs,
+                                             const float2* __restrict__ pts, int n, float pt_factor, float* __restrict__ prod) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float2 p = pts[i];
+    float gx, gy, rot, fv;
+    hs_point_terms(val, L, ex, ey, sn, cs, p.x * pt_factor, p.y * pt_factor, gx, gy, rot, fv);
+    float* q = prod + i * HS_NPROD;
+    q[0] = gx * fv;   // dTr[0]
+    q[1] = gy * fv;   // dTr[1]
+    q[2] = rot * fv;  // dTr[2]
+    q[3] = gx * gx;   // H(0,0)
+    q[4] = gy * gy;   // H(1,1)
+    q[5] = rot * rot; // H(2,2)
+    q[6] = gx * gy;   // H(0,1)
+    q[7] = gx * rot;  // H(0,2)
+    q[8] = gy * rot;  // H(1,2)
+  }
+  __syncthreads();
   HsAcc a = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  if (!STRICT) {
-#pragma unroll 2
-    for (int i = lane; i < n; i += 32) {
-      float2 p = pts[i];
-      float gx, gy, rot, fv;
-      hs_point_terms(val, L, ex, ey, sn, cs, p.x * pt_factor, p.y * pt_factor, gx, gy, rot, fv);
-      hs_acc_add(a, gx, gy, rot, fv);
-    }
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    float acc = 0.0f;
+    if (STRICT) {
+      if (lane < HS_NPROD) {
+        const float* q = prod + lane;
+        int i = 0;
+        for (; i + 8 <= n; i += 8) {  // loads are independent of the chain and issue ahead of it
+          float t0 = q[(i + 0) * HS_NPROD], t1 = q[(i + 1) * HS_NPROD], t2 = q[(i + 2) * HS_NPROD], t3 = q[(i + 3) * HS_NPROD];
+          float t4 = q[(i + 4) * HS_NPROD], t5 = q[(i + 5) * HS_NPROD], t6 = q[(i + 6) * HS_NPROD], t7 = q[(i + 7) * HS_NPROD];
+          acc += t0; acc += t1; acc += t2; acc += t3; acc += t4; acc += t5; acc += t6; acc += t7;
+        }
+        for (; i < n; ++i) acc += q[i * HS_NPROD];
+      }
+      a.d0 = __shfl_sync(0xffffffffu, acc, 0);
+      a.d1 = __shfl_sync(0xffffffffu, acc, 1);
+      a.d2 = __shfl_sync(0xffffffffu, acc, 2);
+      a.h00 = __shfl_sync(0xffffffffu, acc, 3);
+      a.h11 = __shfl_sync(0xffffffffu, acc, 4);
+      a.h22 = __shfl_sync(0xffffffffu, acc, 5);
+      a.h01 = __shfl_sync(0xffffffffu, acc, 6);
+      a.h02 = __shfl_sync(0xffffffffu, acc, 7);
+      a.h12 = __shfl_sync(0xffffffffu, acc, 8);
+    } else {
+      float r[HS_NPROD];
 #pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) {
-      a.d0 += __shfl_xor_sync(0xffffffffu, a.d0, m);
-      a.d1 += __shfl_xor_sync(0xffffffffu, a.d1, m);
-      a.d2 += __shfl_xor_sync(0xffffffffu, a.d2, m);
-      a.h00 += __shfl_xor_sync(0xffffffffu, a.h00, m);
-      a.h11 += __shfl_xor_sync(0xffffffffu, a.h11, m);
-      a.h22 += __shfl_xor_sync(0xffffffffu, a.h22, m);
-      a.h01 += __shfl_xor_sync(0xffffffffu, a.h01, m);
-      a.h02 += __shfl_xor_sync(0xffffffffu, a.h02, m);
-      a.h12 += __shfl_xor_sync(0xffffffffu, a.h12, m);
-    }
-  } else {
-    for (int i0 = 0; i0 < n; i0 += 32) {
-      int i = i0 + lane;
-      float gx = 0.f, gy = 0.f, rot = 0.f, fv = 0.f;
-      if (i < n) {
-        float2 p = pts[i];
-        hs_point_terms(val, L, ex, ey, sn, cs, p.x * pt_factor, p.y * pt_factor, gx, gy, rot, fv);
+      for (int k = 0; k < HS_NPROD; ++k) r[k] = 0.0f;
+      for (int i = lane; i < n; i += 32) {
+#pragma unroll
+        for (int k = 0; k < HS_NPROD; ++k) r[k] += prod[i * HS_NPROD + k];
       }
-      int cnt = min(32, n - i0);
-      for (int l = 0; l < cnt; ++l) {
-        float g0 = __shfl_sync(0xffffffffu, gx, l), g1 = __shfl_sync(0xffffffffu, gy, l);
-        float r0 = __shfl_sync(0xffffffffu, rot, l), f0 = __shfl_sync(0xffffffffu, fv, l);
-        hs_acc_add(a, g0, g1, r0, f0);
+#pragma unroll
+      for (int m = 16; m >= 1; m >>= 1) {
+#pragma unroll
+        for (int k = 0; k < HS_NPROD; ++k) r[k] += __shfl_xor_sync(0xffffffffu, r[k], m);
       }
+      a.d0 = r[0]; a.d1 = r[1]; a.d2 = r[2]; a.h00 = r[3]; a.h11 = r[4]; a.h22 = r[5]; a.h01 = r[6]; a.h02 = r[7]; a.h12 = r[8];
     }
   }
   return a;
@@ -267,21 +295,28 @@ __device__ __forceinline__ bool hs_gauss_newton_step(const HsAcc& a, float& ex, 
 // k_match: HectorSlamProcessor::update minus the ray-cast (HSL/slam_main/HectorSlamProcessor.h:71-95):
 //   MapRepMultiMap::matchData (MapRepMultiMap.h:116-132) -> ScanMatcher::matchData per level, coarse to fine
 //   (ScanMatcher.h:54-190), then the poseDifferenceLargerThan gate and the per-stream bookkeeping.
-// One warp owns one stream for the whole coarse-to-fine solve; nothing returns to the host in between.
+// One CTA owns one stream for the whole coarse-to-fine solve (14 evaluations for 3 levels); the pose estimate
+// lives in shared memory and nothing returns to the host in between. Warp 0 carries the serial part
+// (sums, 3x3 solve, sin/cos of the new angle); the other warps only help with the per-point gathers.
 // mode: 0 = update (match + gate), 1 = match only (no gate, no integration).
+// dynamic shared memory: max_points * 9 floats.
+#define HS_MATCH_THREADS 128
+
 template <bool STRICT>
-__global__ void __launch_bounds__(128) k_match(HsParams P, int n_slots, const int32_t* __restrict__ stream_ids,
-                                               const float2* __restrict__ points, const int32_t* __restrict__ counts,
-                                               const float2* __restrict__ origos, const float* __restrict__ hints,
-                                               const uint8_t* __restrict__ mwm_flags, int mode) {
-  int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  int lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(HS_MATCH_THREADS) k_match(HsParams P, int n_slots, const int32_t* __restrict__ stream_ids,
+                                                            const float2* __restrict__ points, const int32_t* __restrict__ counts,
+                                                            const float2* __restrict__ origos, const float* __restrict__ hints,
+                                                            const uint8_t* __restrict__ mwm_flags, int mode) {
+  extern __shared__ float hs_prod[];
+  __shared__ float s_est[5];  // ex, ey, eth, sin(eth), cos(eth)
+  const int slot = blockIdx.x;
+  const int tid = threadIdx.x;
   if (slot >= n_slots) return;
-  int s = hs_slot_stream(stream_ids, slot);
+  const int s = hs_slot_stream(stream_ids, slot);
   int n = counts[slot];
   n = n < 0 ? 0 : (n > P.max_points ? P.max_points : n);
   const float2* pts = points + (size_t)slot * P.max_points;
-  bool mwm = mwm_flags ? (mwm_flags[slot] != 0) : false;
+  const bool mwm = mwm_flags ? (mwm_flags[slot] != 0) : false;
   float wx, wy, wth;
   if (hints) { wx = hints[3 * slot]; wy = hints[3 * slot + 1]; wth = hints[3 * slot + 2]; }
   else { wx = P.last_pose[3 * s]; wy = P.last_pose[3 * s + 1]; wth = P.last_pose[3 * s + 2]; }
@@ -290,8 +325,8 @@ __global__ void __launch_bounds__(128) k_match(HsParams P, int n_slots, const in
     // dataContainers[level-1].setFrom(dataContainer, 2^-level) (MapRepMultiMap.h:127): keep the level-0
     // points of the last matched scan; the power-of-two factor is applied (exactly) where they are used.
     float2* cp = reinterpret_cast<float2*>(P.coarse_pts) + (size_t)s * P.max_points;
-    for (int i = lane; i < n; i += 32) cp[i] = pts[i];
-    if (lane == 0) {
+    for (int i = tid; i < n; i += blockDim.x) cp[i] = pts[i];
+    if (tid == 0) {
       P.coarse_cnt[s] = n;
       float2 o = origos ? origos[slot] : make_float2(0.f, 0.f);
       P.coarse_origo[2 * s] = o.x;
@@ -304,17 +339,28 @@ __global__ void __launch_bounds__(128) k_match(HsParams P, int n_slots, const in
       for (int level = P.n_levels - 1; level >= 0; --level) {
         const HsLevel& L = P.lv[level];
         const float* val = val_s + L.cell_offset;
-        float ex, ey, eth = wth;
-        hs_world_to_map(L, wx, wy, ex, ey);
-        for (int it = 0; it <= L.max_iter; ++it) {  // 1 + maxIterations evaluations, no early exit
-          a = hs_eval_warp<STRICT>(val, L, ex, ey, eth, pts, n, L.pt_factor, lane);
-          clamps += hs_gauss_newton_step(a, ex, ey, eth) ? 1u : 0u;
+        float ex = 0.f, ey = 0.f, eth = wth;
+        if (tid < 32) {
+          hs_world_to_map(L, wx, wy, ex, ey);
+          if (tid == 0) { s_est[0] = ex; s_est[1] = ey; s_est[2] = eth; s_est[3] = hs_sinf(eth); s_est[4] = hs_cosf(eth); }
         }
-        eth = hs_normalize_angle(eth);
-        hs_map_to_world(L, ex, ey, wx, wy);
-        wth = eth;
+        __syncthreads();
+        for (int it = 0; it <= L.max_iter; ++it) {  // 1 + maxIterations evaluations, no early exit
+          const float cex = s_est[0], cey = s_est[1], csn = s_est[3], ccs = s_est[4];
+          a = hs_eval_cta<STRICT>(val, L, cex, cey, csn, ccs, pts, n, L.pt_factor, hs_prod);
+          if (tid < 32) {
+            clamps += hs_gauss_newton_step(a, ex, ey, eth) ? 1u : 0u;
+            if (tid == 0) { s_est[0] = ex; s_est[1] = ey; s_est[2] = eth; s_est[3] = hs_sinf(eth); s_est[4] = hs_cosf(eth); }
+          }
+          __syncthreads();
+        }
+        if (tid < 32) {
+          eth = hs_normalize_angle(eth);
+          hs_map_to_world(L, ex, ey, wx, wy);
+          wth = eth;
+        }
       }
-      if (lane == 0) {
+      if (tid == 0) {
         float* c = P.cov + 9 * (size_t)s;  // covMatrix = H of the last evaluation (ScanMatcher.h:184)
         c[0] = a.h00; c[1] = a.h01; c[2] = a.h02;
         c[3] = a.h01; c[4] = a.h11; c[5] = a.h12;
@@ -323,7 +369,7 @@ __global__ void __launch_bounds__(128) k_match(HsParams P, int n_slots, const in
       }
     }
   }
-  if (lane == 0) {
+  if (tid == 0) {
     P.last_pose[3 * s] = wx; P.last_pose[3 * s + 1] = wy; P.last_pose[3 * s + 2] = wth;
     int integrate = 0;
     if (mode == 0) {
@@ -373,18 +419,19 @@ __global__ void __launch_bounds__(128) k_force_integrate(HsParams P, int n_slots
 }
 
 // k_hessian_derivs: getCompleteHessianDerivs for many pose hypotheses against one stream's level
-// (BASELINE config 4). One warp per pose; pts are already scaled to the level.
+// (BASELINE config 4). One CTA per pose; pts are already scaled to the level. dynamic smem: n_pts * 9 floats.
 template <bool STRICT>
-__global__ void __launch_bounds__(128) k_hessian_derivs(HsParams P, int stream, int level, const float* __restrict__ poses_map,
-                                                        int n_poses, const float2* __restrict__ pts, int n_pts,
-                                                        float* __restrict__ H9, float* __restrict__ dTr3) {
-  int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  int lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(HS_MATCH_THREADS) k_hessian_derivs(HsParams P, int stream, int level, const float* __restrict__ poses_map,
+                                                                     int n_poses, const float2* __restrict__ pts, int n_pts,
+                                                                     float* __restrict__ H9, float* __restrict__ dTr3) {
+  extern __shared__ float hs_prod[];
+  const int k = blockIdx.x;
   if (k >= n_poses) return;
   const HsLevel& L = P.lv[level];
   const float* val = P.val + (size_t)stream * P.cells_per_stream + L.cell_offset;
-  HsAcc a = hs_eval_warp<STRICT>(val, L, poses_map[3 * k], poses_map[3 * k + 1], poses_map[3 * k + 2], pts, n_pts, 1.0f, lane);
-  if (lane == 0) {
+  const float th = poses_map[3 * k + 2];
+  HsAcc a = hs_eval_cta<STRICT>(val, L, poses_map[3 * k], poses_map[3 * k + 1], hs_sinf(th), hs_cosf(th), pts, n_pts, 1.0f, hs_prod);
+  if (threadIdx.x == 0) {
     float* h = H9 + 9 * (size_t)k;
     h[0] = a.h00; h[1] = a.h01; h[2] = a.h02;
     h[3] = a.h01; h[4] = a.h11; h[5] = a.h12;
@@ -402,57 +449,110 @@ __global__ void __launch_bounds__(128) k_hessian_derivs(HsParams P, int stream, 
 //   io = smallest beam index whose END POINT is the cell, jf = smallest beam index whose FREE trace crosses it.
 //   io exists: idx = markOcc, v' = (jf < io ? (v + f) - f : v), then v' += o if v' < 50.
 //   only jf:   idx = markFree, v += f.                      
-// Every stored updateIndex is < markFree when a scan starts (currUpdateIndex grows by 3 per scan), so the
-// marker word is free to serve as scratch during the scan as long as its final value is exact. One CTA
-// owns one (stream, level) and runs three barrier-separated phases over all beams:
-//   A  end points:  atomicMin(idx[end], TEMP | beam<<1)        -> io per end cell
-//   B  free traces: cell still < markFree  -> atomicMax(idx, markFree); the unique winner adds f to val
-//                   cell holds TEMP and this beam < io -> atomicOr(idx, 1)  (the "free came first" flag)
-//   C  end points:  the beam that owns io applies undo/occupied to val and stores markOcc.
-// A beam's own trace never contains its own end point (bresenham2D visits abs_da cells from the start).
+// Every stored updateIndex is < markFree when a scan starts (currUpdateIndex grows by 3 per scan): a cell whose
+// marker is rewritten during a scan needs no look at its old marker, "touched this scan" is the only fact it holds.
+//
+// One CTA owns one (stream, level) and runs barrier-separated phases over all beams; everything the beams
+// share while the scan is being traced lives in SHARED memory, the grids in HBM only see the final,
+// coalesced updates:
+//   A1  per beam: end cell, Bresenham parameters -> beam record; bounding box of the scan
+//   A2  per beam: end cell -> shared hash table (cell -> smallest beam index io, via atomicMin) and the
+//       end-cell bit plane of the CTA's cell map
+//   B1  free cells of all beams. bresenham2D's state after t steps has the closed form
+//           cell(t) = k0 + t*off_a + floor((abs_da/2 + t*abs_db) / abs_da) * off_b,   t = 0 .. abs_da-1,
+//       so the free cells of a beam are independent work items: a group of G adjacent lanes (G = 32, 16, 8 on
+//       levels 0, 1, 2+) owns one beam at a time, lane j takes t = j, j+G, ... and advances the error term G
+//       steps at once. Marks go to a bit-per-cell plane of the bounding box (shared-memory atomicOr, skipped when
+//       the bit is already set); the ~49 k scattered cell visits of a scan never reach L2/HBM. A free cell that is some beam's end cell
+//       (end-cell plane) looks io up in the hash table and, if this beam < io, sets the entry's
+//       "free came first" flag.
+//   B2  coalesced sweep of the box: free bit set -> idx = markFree, val += f  (exactly once per cell)
+//   C   end points: the beam that owns io applies undo-free / occupied to val and stores markOcc.
+// If the bounding box does not fit the cell map (HS_PLANE_BYTES per plane) B1/B2 fall back to marking in the
+// global marker plane: idx = markFree by plain store (idempotent), then the sweep applies f where
+// idx == markFree (only this scan can have written that value); end cells are recognised by a hash probe.
+// No scratch value is ever stored in the grids, and no global atomic is used. A beam's own trace never
+// contains its own end point (bresenham2D visits abs_da cells from the start).
 
-#define HS_TEMP_BASE ((int)0x80000000)  // TEMP values are < -1, every legitimate marker is >= -1
+#define HS_HASH_EMPTY (-1)
+#define HS_PLANE_BYTES 24576              // one bit plane of the shared-memory cell map (196608 cells, e.g. 443^2)
+#define HS_MAP_BYTES (2 * HS_PLANE_BYTES)  // plane 0: crossed by a free trace, plane 1: some beam's end cell
+#define HS_RAYCAST_THREADS 256
 
 struct HsBeam {
   int valid;            // begin != end and both inside the grid
-  int k0;               // start cell offset
+  int ex, ey;           // end cell
   int kend;             // end cell offset
   unsigned abs_da, abs_db;
-  int off_a, off_b;
+  int a_is_x, sa, sb;   // dominant axis, step signs along the dominant / minor axis
 };
 
+// updateByScan's per-beam arithmetic (OccGridMapBase.h:145-158) + updateLineBresenhami's set-up (:170-206)
 __device__ __forceinline__ HsBeam hs_make_beam(const HsLevel& L, int bx, int by, float mpx, float mpy, float sn, float cs,
                                               float px, float py) {
   HsBeam b;
   float exf = ((cs * px + (-sn) * py) + mpx) + 0.5f;
   float eyf = ((sn * px + cs * py) + mpy) + 0.5f;
   int ex = (int)exf, ey = (int)eyf;  // truncation toward zero, like cast<int>() (OccGridMapBase.h:152-155)
+  b.ex = ex;
+  b.ey = ey;
   b.valid = (bx != ex || by != ey) && bx >= 0 && bx < L.sx && by >= 0 && by < L.sy && ex >= 0 && ex < L.sx && ey >= 0 && ey < L.sy;
   int dx = ex - bx, dy = ey - by;
   unsigned abs_dx = (unsigned)abs(dx), abs_dy = (unsigned)abs(dy);
-  int off_dx = dx > 0 ? 1 : -1;             // util::sign: sign(0) = -1 (UtilFunctions.h:56-59)
-  int off_dy = (dy > 0 ? 1 : -1) * L.sx;
-  b.k0 = by * L.sx + bx;
+  int sdx = dx > 0 ? 1 : -1;             // util::sign: sign(0) = -1 (UtilFunctions.h:56-59)
+  int sdy = dy > 0 ? 1 : -1;
   b.kend = ey * L.sx + ex;
-  if (abs_dx >= abs_dy) { b.abs_da = abs_dx; b.abs_db = abs_dy; b.off_a = off_dx; b.off_b = off_dy; }
-  else { b.abs_da = abs_dy; b.abs_db = abs_dx; b.off_a = off_dy; b.off_b = off_dx; }
+  if (abs_dx >= abs_dy) { b.abs_da = abs_dx; b.abs_db = abs_dy; b.a_is_x = 1; b.sa = sdx; b.sb = sdy; }
+  else { b.abs_da = abs_dy; b.abs_db = abs_dx; b.a_is_x = 0; b.sa = sdy; b.sb = sdx; }
   return b;
 }
 
-__device__ __forceinline__ void hs_mark_free(float* __restrict__ val, int* __restrict__ idx, int k, int beam, int mark_free, float f) {
-  int w = __ldcg(idx + k);
-  if (w < -1) {                                   // TEMP: an end point lives here
-    int io = (w - HS_TEMP_BASE) >> 1;
-    if (beam < io && !(w & 1)) atomicOr(idx + k, 1);
-  } else if (w < mark_free) {
-    int old = atomicMax(idx + k, mark_free);
-    if (old < mark_free) val[k] = val[k] + f;     // updateSetFree, exactly once per cell and scan
+// Beam record kept in shared memory between the phases (one per scan point), 12 bytes.
+struct HsBeamRec {
+  int kend;                    // end cell offset in the grid
+  unsigned short da, db, rg;   // abs_da (0 marks a dropped beam), abs_db, (G*abs_db) % abs_da
+  unsigned char qg;            // (G*abs_db) / abs_da: the error-term advance of G steps at once
+  unsigned char flags;         // bit0: dominant axis is x, bit1: step along a is +, bit2: step along b is +
+};
+
+// exact x / d for 0 <= x < 2^24, 0 < d < 2^24 (float reciprocal + one-step correction)
+__device__ __forceinline__ int hs_udiv_small(int x, int d, int& rem) {
+  int q = (int)((float)x * (1.0f / (float)d));
+  int r = x - q * d;
+  if (r < 0) { --q; r += d; }
+  else if (r >= d) { ++q; r -= d; }
+  rem = r;
+  return q;
+}
+
+// End-cell hash table in shared memory: open addressing, linear probing, size = power of two >= 2 * max_points.
+__device__ __forceinline__ int hs_hash_slot(int cell, int log2_size) { return (int)(((unsigned)cell * 2654435761u) >> (32 - log2_size)); }
+
+// returns the slot of `cell`, or -1 if the cell is not an end cell
+__device__ __forceinline__ int hs_hash_find(const int* __restrict__ keys, int mask, int log2_size, int cell) {
+  int h = hs_hash_slot(cell, log2_size);
+  for (;;) {
+    int k = keys[h];
+    if (k == cell) return h;
+    if (k == HS_HASH_EMPTY) return -1;
+    h = (h + 1) & mask;
   }
 }
 
-__global__ void __launch_bounds__(256) k_raycast(HsParams P, int n_slots, const int32_t* __restrict__ stream_ids,
-                                                 const float2* __restrict__ points, const int32_t* __restrict__ counts,
-                                                 const float2* __restrict__ origos) {
+// dynamic shared memory: HS_MAP_BYTES (cell map) | hash keys[T] | hash vals[T] | max_points * sizeof(HsBeamRec),
+// T = hash_size (power of two >= 2 * max_points).
+__global__ void __launch_bounds__(HS_RAYCAST_THREADS) k_raycast(HsParams P, int n_slots, const int32_t* __restrict__ stream_ids,
+                                                                const float2* __restrict__ points, const int32_t* __restrict__ counts,
+                                                                const float2* __restrict__ origos, int log2_hash) {
+  extern __shared__ __align__(16) unsigned char hs_smem[];
+  const int hash_size = 1 << log2_hash, hash_mask = hash_size - 1;
+  unsigned* fmap = reinterpret_cast<unsigned*>(hs_smem);                   // free-trace bits
+  unsigned* emap = reinterpret_cast<unsigned*>(hs_smem + HS_PLANE_BYTES);  // end-cell bits
+  int* hkeys = reinterpret_cast<int*>(hs_smem + HS_MAP_BYTES);             // end cell (grid offset) or EMPTY
+  int* hvals = hkeys + hash_size;                                          // (io << 1) | free-came-first flag
+  HsBeamRec* beams = reinterpret_cast<HsBeamRec*>(hvals + hash_size);
+  __shared__ int s_box[4];  // xmin, ymin, xmax, ymax over the start cell and all valid end cells
+
   int slot = blockIdx.x / P.n_levels;
   int level = blockIdx.x - slot * P.n_levels;
   if (slot >= n_slots) return;
@@ -461,6 +561,7 @@ __global__ void __launch_bounds__(256) k_raycast(HsParams P, int n_slots, const 
   const HsLevel& L = P.lv[level];
   float* val = P.val + (size_t)s * P.cells_per_stream + L.cell_offset;
   int* idx = P.idx + (size_t)s * P.cells_per_stream + L.cell_offset;
+  const int W = L.sx;
 
   // level 0 integrates the scan itself, level i > 0 the container last refreshed by matchData
   // (MapRepMultiMap.h:134-147) -- possibly stale or empty when map_without_matching was used.
@@ -487,52 +588,205 @@ __global__ void __launch_bounds__(256) k_raycast(HsParams P, int n_slots, const 
   hs_world_to_map(L, P.slot_pose[3 * slot], P.slot_pose[3 * slot + 1], mpx, mpy);
   float th = P.slot_pose[3 * slot + 2];
   float sn = hs_sinf(th), cs = hs_cosf(th);
-  int bx = (int)(((cs * ox + (-sn) * oy) + mpx) + 0.5f);  // Vector2i(float, float): truncation (OccGridMapBase.h:137)
-  int by = (int)(((sn * ox + cs * oy) + mpy) + 0.5f);
+  const int bx = (int)(((cs * ox + (-sn) * oy) + mpx) + 0.5f);  // Vector2i(float, float): truncation (OccGridMapBase.h:137)
+  const int by = (int)(((sn * ox + cs * oy) + mpy) + 0.5f);
   const float pf = L.pt_factor;
+  const int G = level == 0 ? 32 : (level == 1 ? 16 : 8);
+  const int lane = threadIdx.x & 31;
 
-  // phase A: end points
+  // clear the cell map and the hash table (independent of everything else), reset the box
+  {
+    uint4* m4 = reinterpret_cast<uint4*>(hs_smem);
+    for (int i = threadIdx.x; i < HS_MAP_BYTES / 16; i += blockDim.x) m4[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = threadIdx.x; i < hash_size; i += blockDim.x) { hkeys[i] = HS_HASH_EMPTY; hvals[i] = INT_MAX; }
+    if (threadIdx.x == 0) { s_box[0] = INT_MAX; s_box[1] = INT_MAX; s_box[2] = INT_MIN; s_box[3] = INT_MIN; }
+  }
+  __syncthreads();
+
+  // phase A1: one thread per beam -- beam record and bounding box
   unsigned visits = 0;
+  int xmin = INT_MAX, ymin = INT_MAX, xmax = INT_MIN, ymax = INT_MIN;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     float2 p = pts[i];
     HsBeam b = hs_make_beam(L, bx, by, mpx, mpy, sn, cs, p.x * pf, p.y * pf);
+    HsBeamRec r;
+    r.kend = b.kend; r.da = 0; r.db = (unsigned short)b.abs_db; r.rg = 0; r.qg = 0;
+    r.flags = (unsigned char)((b.a_is_x ? 1 : 0) | (b.sa > 0 ? 2 : 0) | (b.sb > 0 ? 4 : 0));
     if (b.valid) {
-      atomicMin(idx + b.kend, HS_TEMP_BASE + (i << 1));
       visits += b.abs_da + 1u;
+      r.da = (unsigned short)b.abs_da;
+      int rg;
+      r.qg = (unsigned char)hs_udiv_small(G * (int)b.abs_db, (int)b.abs_da, rg);
+      r.rg = (unsigned short)rg;
+      xmin = min(xmin, b.ex); xmax = max(xmax, b.ex); ymin = min(ymin, b.ey); ymax = max(ymax, b.ey);
     }
+    beams[i] = r;
   }
   visits = __reduce_add_sync(0xffffffffu, visits);
-  if ((threadIdx.x & 31) == 0 && visits) atomicAdd(&P.counters[3], (unsigned long long)visits);
+  xmin = __reduce_min_sync(0xffffffffu, xmin); ymin = __reduce_min_sync(0xffffffffu, ymin);
+  xmax = __reduce_max_sync(0xffffffffu, xmax); ymax = __reduce_max_sync(0xffffffffu, ymax);
+  if (lane == 0 && visits) {
+    atomicAdd(&P.counters[3], (unsigned long long)visits);
+    atomicMin(&s_box[0], min(xmin, bx)); atomicMin(&s_box[1], min(ymin, by));
+    atomicMax(&s_box[2], max(xmax, bx)); atomicMax(&s_box[3], max(ymax, by));
+  }
   __syncthreads();
-  // phase B: free traces (bresenham2D, OccGridMapBase.h:243-260)
+  if (s_box[2] < s_box[0]) return;  // no valid beam (uniform for the CTA)
+
+  // geometry of the cell map: rows of pw 32-cell words starting at a 32-aligned x0; pw odd so that a vertical
+  // run of cells spreads over the shared-memory banks
+  const int x0 = s_box[0] & ~31, y0 = s_box[1], x1 = s_box[2], y1 = s_box[3];
+  const int bh = y1 - y0 + 1;
+  const int pw = (((x1 - x0) >> 5) + 1) | 1;
+  const int pitch = pw << 5;  // cells per map row
+  const bool use_map = (long long)pw * bh * 4 <= HS_PLANE_BYTES;
+
+  // phase A2: end point ownership -- io = smallest beam index per end cell
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    float2 p = pts[i];
-    HsBeam b = hs_make_beam(L, bx, by, mpx, mpy, sn, cs, p.x * pf, p.y * pf);
-    if (!b.valid) continue;
-    int k = b.k0;
-    int err = (int)(b.abs_da / 2);
-    hs_mark_free(val, idx, k, i, mark_free, f);
-    unsigned end = b.abs_da - 1;
-    for (unsigned t = 0; t < end; ++t) {
-      k += b.off_a;
-      err += (int)b.abs_db;
-      if ((unsigned)err >= b.abs_da) { k += b.off_b; err -= (int)b.abs_da; }
-      hs_mark_free(val, idx, k, i, mark_free, f);
+    const HsBeamRec r = beams[i];
+    if (r.da == 0) continue;
+    int h = hs_hash_slot(r.kend, log2_hash);
+    for (;;) {
+      int old = atomicCAS(&hkeys[h], HS_HASH_EMPTY, r.kend);
+      if (old == HS_HASH_EMPTY || old == r.kend) break;
+      h = (h + 1) & hash_mask;
+    }
+    atomicMin(&hvals[h], i << 1);
+    if (use_map) {
+      int ey = r.kend / W, ex = r.kend - ey * W;
+      int kb = (ey - y0) * pitch + (ex - x0);
+      atomicOr(&emap[kb >> 5], 1u << (kb & 31));
     }
   }
   __syncthreads();
-  // phase C: end points
+
+  // phase B1: free cells (bresenham2D, OccGridMapBase.h:243-260), G lanes per beam
+  {
+    const int j = threadIdx.x & (G - 1);
+    const int group = threadIdx.x / G, n_groups = blockDim.x / G;
+    const int row_step = use_map ? pitch : W;                       // address step of one cell in y
+    const int k0 = use_map ? (by - y0) * pitch + (bx - x0) : by * W + bx;
+    for (int i0 = 0; i0 < n; i0 += n_groups) {                       // same trip count for every thread of the CTA
+      const int i = i0 + group;
+      int da = 0, db = 0, rg = 0, off_b = 0, kstep = 0, k = 0, err = 0;
+      if (i < n) {
+        const HsBeamRec r = beams[i];
+        if (j < (int)r.da) {
+          da = r.da; db = r.db; rg = r.rg;
+          const int sa = (r.flags & 2) ? 1 : -1, sb = (r.flags & 4) ? 1 : -1;
+          const int off_a = (r.flags & 1) ? sa : sa * row_step;
+          off_b = (r.flags & 1) ? sb * row_step : sb;
+          int q = hs_udiv_small((da >> 1) + j * db, da, err);
+          k = k0 + j * off_a + q * off_b;
+          kstep = G * off_a + (int)r.qg * off_b;
+        }
+      }
+      int t = j;
+      if (use_map) {
+        for (;;) {
+          const bool valid = t < da;
+          const unsigned bal = __ballot_sync(0xffffffffu, valid);
+          if (bal == 0u) break;
+          if (valid) {
+            const int widx = k >> 5;
+            const unsigned bit = 1u << (k & 31);
+            const bool is_end = (emap[widx] & bit) != 0u;
+            if (is_end) {
+              // the free trace of beam i crosses a cell that is some beam's end point
+              int xx;
+              int yy = hs_udiv_small(k, pitch, xx);
+              int h = hs_hash_find(hkeys, hash_mask, log2_hash, (yy + y0) * W + (xx + x0));
+              if (h >= 0) {
+                int hv = hvals[h];
+                if (i < (hv >> 1) && !(hv & 1)) atomicOr(&hvals[h], 1);
+              }
+            } else if ((fmap[widx] & bit) == 0u) {
+              atomicOr(&fmap[widx], bit);   // lanes of one warp on the same word serialise in the LSU (~1 cycle each)
+            }
+            t += G;
+            k += kstep;
+            err += rg;
+            if (err >= da) { k += off_b; err -= da; }
+          }
+        }
+      } else {
+        while (t < da) {
+          int kk[4], w[4];
+          int c = 0;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            w[u] = INT_MAX;
+            if (t < da) {
+              kk[u] = k;
+              c = u + 1;
+              int h = hs_hash_find(hkeys, hash_mask, log2_hash, k);
+              if (h >= 0) {                 // end cell: only the "free came first" flag matters
+                int hv = hvals[h];
+                if (i < (hv >> 1) && !(hv & 1)) atomicOr(&hvals[h], 1);
+              } else {
+                w[u] = idx[k];              // may be served by L1: a stale "not yet marked" only repeats an idempotent store
+              }
+              t += G;
+              k += kstep;
+              err += rg;
+              if (err >= da) { k += off_b; err -= da; }
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (u < c && w[u] < mark_free) idx[kk[u]] = mark_free;
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  // phase B2: updateSetFree exactly once per marked cell -- coalesced sweep of the bounding box,
+  // one warp per 32-cell row segment, 8 independent segments in flight per lane
+  {
+    const int warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const int segs = ((x1 - x0) >> 5) + 1;         // 32-cell (128-byte aligned) segments per row
+    const int items = segs * bh;
+    for (int it0 = warp * 8; it0 < items; it0 += n_warps * 8) {
+      int g[8];
+      float v[8];
+      bool on[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        int it = it0 + u;
+        on[u] = false;
+        if (it < items) {
+          int sg;
+          int ry = hs_udiv_small(it, segs, sg);
+          g[u] = (y0 + ry) * W + x0 + (sg << 5) + lane;
+          if (use_map) on[u] = (fmap[ry * pw + sg] >> lane) & 1u;
+          else on[u] = (x0 + (sg << 5) + lane <= x1) && (__ldcg(idx + g[u]) == mark_free);
+          if (on[u]) v[u] = val[g[u]];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (on[u]) {
+          val[g[u]] = v[u] + f;
+          if (use_map) idx[g[u]] = mark_free;
+        }
+      }
+    }
+  }
+
+  // phase C: end points -- the beam that owns io applies undo-free / occupied and stores markOcc
+  // (end cells are disjoint from the cells B2 writes: their free bit / free marker is never set)
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    float2 p = pts[i];
-    HsBeam b = hs_make_beam(L, bx, by, mpx, mpy, sn, cs, p.x * pf, p.y * pf);
-    if (!b.valid) continue;
-    int w = __ldcg(idx + b.kend);
-    if (w < -1 && ((w - HS_TEMP_BASE) >> 1) == i) {
-      float v = val[b.kend];
-      if (w & 1) v = (v + f) - f;        // updateSetFree by an earlier beam, then updateUnsetFree
+    const HsBeamRec r = beams[i];
+    if (r.da == 0) continue;
+    int h = hs_hash_find(hkeys, hash_mask, log2_hash, r.kend);
+    int hv = hvals[h];
+    if ((hv >> 1) == i) {
+      float v = val[r.kend];
+      if (hv & 1) v = (v + f) - f;       // updateSetFree by an earlier beam, then updateUnsetFree
       if (v < 50.0f) v = v + o;          // updateSetOccupied
-      val[b.kend] = v;
-      idx[b.kend] = mark_occ;
+      val[r.kend] = v;
+      idx[r.kend] = mark_occ;
     }
   }
 }
