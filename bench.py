@@ -178,6 +178,7 @@ def main():
     import torch
     import torch.distributed as dist
     import tfe_slam_ucl_b200 as hs
+    from tfe_slam_ucl_b200 import sharding
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl ours needs a CUDA device: hsgpu has no CPU fallback")
@@ -187,7 +188,9 @@ def main():
 
     steps = W + K
     t_gen = time.time()
-    sc, pts, cnt = gen_inputs(hs, S, steps, 0xC0FFEE + rank * S)
+    first_stream, n_local = sharding.shard_range(world * S, world, rank)   # this rank's block of the global streams
+    assert n_local == S
+    sc, pts, cnt = gen_inputs(hs, S, steps, 0xC0FFEE + first_stream)
     t_gen = time.time() - t_gen
 
     eng = hs.Engine(0.05, 1024, 1024, (0.5, 0.5), 3, n_streams=S, max_points=360, device=local_rank)
@@ -235,13 +238,12 @@ def main():
     integrations = st1["integrations"] - st0["integrations"]
     visits = st1["cell_visits"] - st0["cell_visits"]
 
-    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
     agg = torch.tensor([float(integrations), float(visits), float(launches)], dtype=torch.float64, device="cuda")
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(agg, op=dist.ReduceOp.SUM)
-    ms_max = float(t.item())
-    value = world * S * K / (ms_max * 1e-3)
+    total_scans, max_s = sharding.aggregate_throughput(S * K, ms_total * 1e-3, device="cuda")   # sum of units, MAX of times
+    ms_max = max_s * 1e3
+    value = total_scans / max_s
 
     # ---- leg 2: end to end through the host C ABI --------------------------------------------
     eng.reset()
@@ -261,10 +263,8 @@ def main():
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     pose_checksum = float(h_pose.sum())
-    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * S * K / float(te.item())
+    e2e_scans, e2e_max_s = sharding.aggregate_throughput(S * K, e2e_s, device="cuda")
+    e2e_value = e2e_scans / e2e_max_s
     h2d_step = pts_step + cnt_step
     d2h_step = S * 3 * 4
 

@@ -1,0 +1,187 @@
+"""GPU edge cases against the CPU oracle, bit for bit: empty and ragged scans, beams leaving the map, pose hints,
+map_without_matching (stale coarse containers), reset, stream subsets via stream_ids, the LaserScan-ranges entry
+point, the large-bounding-box fallback of the ray-caster, map upload/download/classification, and the
+size-independent properties used at BASELINE sizes."""
+import numpy as np
+import pytest
+
+from hs_testutil import bits, make_streams
+
+pytestmark = pytest.mark.gpu
+
+
+def setup_pair(hs, oracle, n, size=1024, levels=3, res=0.05, max_points=360, free=0.4, occ=0.9, dist=0.0, ang=0.0, start=(0.5, 0.5)):
+    eng = hs.Engine(res, size, size, start, levels, n_streams=n, max_points=max_points)
+    procs = [oracle.CpuProcessor("port", res, size, size, start, levels) for _ in range(n)]
+    for p in procs + [eng]:
+        p.set_update_factor_free(free); p.set_update_factor_occupied(occ)
+        p.set_map_update_min_dist_diff(dist); p.set_map_update_min_angle_diff(ang)
+    return eng, procs
+
+
+def assert_same_maps(eng, procs, levels, streams=None):
+    for s, p in enumerate(procs):
+        gs = s if streams is None else streams[s]
+        for l in range(levels):
+            g, c = eng.download_level(gs, l), p.download_level(l)
+            assert np.array_equal(g["updateIndex"], c["updateIndex"]), "stream %d level %d markers" % (s, l)
+            assert np.array_equal(bits(g["logOddsVal"]), bits(c["logOddsVal"])), "stream %d level %d log-odds" % (s, l)
+
+
+def test_ragged_empty_hints_flags_and_reset(hs, oracle):
+    n, n_scans = 5, 36
+    sc, ranges, pts, cnt, truth = make_streams(hs, n, n_scans, seed0=2024)
+    ranges = ranges.copy()
+    rng = np.random.default_rng(1)
+    ranges[rng.random(ranges.shape) < 0.2] = np.inf
+    ranges[5, 0, :] = np.inf; ranges[6, 0, :] = np.inf          # empty scans
+    ranges[9, 2, 40:] = 0.01                                     # nearly empty
+    pts, cnt = hs.scan_to_points_host(ranges, sc, 20.0)
+    eng, procs = setup_pair(hs, oracle, n, dist=0.4, ang=0.9)
+    poses = np.zeros((n, 3), np.float32)
+    for k in range(n_scans):
+        flags = np.array([(k % 8 == 7) and (s % 2 == 0) for s in range(n)], np.uint8)
+        if k == 20:
+            eng.reset(); [p.reset() for p in procs]; poses[:] = 0
+        if k == 28:
+            eng.reset(3); procs[3].reset(); poses[3] = 0
+        hints = poses + (rng.normal(0, 0.01, poses.shape).astype(np.float32) if k % 5 == 4 else 0)
+        hints = hints.astype(np.float32)
+        out, cov = eng.update_batch(pts[k], cnt[k], pose_hints=hints, map_without_matching=flags)
+        for s, p in enumerate(procs):
+            ref = p.update(pts[k, s], cnt[k, s], hint=hints[s], map_without_matching=bool(flags[s]))
+            assert np.array_equal(bits(out[s]), bits(ref)), (k, s, out[s], ref)
+            if cnt[k, s] and not flags[s]:
+                assert np.array_equal(bits(cov[s]), bits(p.cov()))
+            assert eng.update_index(s, 0) == p.update_index(0)
+        poses = out
+        assert np.array_equal(bits(eng.last_map_update_poses()), bits(np.stack([p.last_map_update_pose() for p in procs])))
+    assert_same_maps(eng, procs, 3)
+    eng.close()
+
+
+def test_beams_leaving_the_map_and_offset_origo(hs, oracle):
+    """Small map + start near a corner: many end points and the start fall outside -> whole beams dropped."""
+    n = 3
+    sc, ranges, pts, cnt, truth = make_streams(hs, n, 12, seed0=99, scale_to_map=20.0)
+    eng, procs = setup_pair(hs, oracle, n, size=128, levels=3, start=(0.2, 0.9))
+    origos = np.array([[0.0, 0.0], [3.5, -2.25], [2000.0, 0.0]], np.float32)   # last: start cell outside the map
+    poses = np.zeros((n, 3), np.float32)
+    for k in range(12):
+        out, _ = eng.update_batch(pts[k], cnt[k], origos=origos, pose_hints=poses)
+        for s, p in enumerate(procs):
+            ref = p.update(pts[k, s], cnt[k, s], origo=origos[s], hint=poses[s])
+            assert np.array_equal(bits(out[s]), bits(ref))
+        poses = out
+    assert_same_maps(eng, procs, 3)
+    assert (eng.download_level(2, 0)["updateIndex"] == -1).all()      # nothing was ever integrated for stream 2
+    eng.close()
+
+
+def test_stream_ids_subset_and_permutation(hs, oracle):
+    n_eng, n_scans = 6, 10
+    sc, ranges, pts, cnt, truth = make_streams(hs, 3, n_scans, seed0=7)
+    ids = np.array([4, 0, 2], np.int32)
+    eng, procs = setup_pair(hs, oracle, 3)
+    eng.close()
+    eng = hs.Engine(n_streams=n_eng, max_points=360)
+    eng.set_update_factor_free(0.4); eng.set_update_factor_occupied(0.9)
+    eng.set_map_update_min_dist_diff(0.0); eng.set_map_update_min_angle_diff(0.0)
+    for k in range(n_scans):
+        out, cov = eng.update_batch(pts[k], cnt[k], stream_ids=ids)
+        for s, p in enumerate(procs):
+            ref = p.update(pts[k, s], cnt[k, s], hint=(out[s] * 0 if k == 0 else prev[s]))
+            assert np.array_equal(bits(out[s]), bits(ref))
+            assert np.array_equal(bits(cov[s]), bits(p.cov())) or k == 0
+        prev = out
+    assert_same_maps(eng, procs, 3, streams=list(ids))
+    for untouched in (1, 3, 5):
+        assert (eng.download_level(untouched, 0)["updateIndex"] == -1).all()
+        assert not eng.poses(untouched, 1).any()
+    with pytest.raises(hs.HsError):
+        eng.update_batch(pts[0], cnt[0], stream_ids=np.array([0, 1, 6], np.int32))
+    eng.close()
+
+
+def test_ranges_entry_point_equals_points_entry_point(hs, oracle):
+    """k_scan_to_points (LaserScan ranges on the device) == host conversion + update, incl. dropped ranges."""
+    n, n_scans = 4, 15
+    sc, ranges, pts, cnt, truth = make_streams(hs, n, n_scans, seed0=31)
+    ranges = ranges.copy()
+    rng = np.random.default_rng(2)
+    ranges[rng.random(ranges.shape) < 0.25] = np.inf
+    ranges[3, 1, :] = 0.0
+    pts, cnt = hs.scan_to_points_host(ranges, sc, 20.0)
+    eng, procs = setup_pair(hs, oracle, n)
+    with pytest.raises(hs.HsError):
+        eng.update_batch_ranges(ranges[0])
+    eng.set_scan_geometry(sc.n_beams, sc.angle_min, sc.angle_increment, sc.range_min, sc.range_max)
+    for k in range(n_scans):
+        out, cov = eng.update_batch_ranges(ranges[k])
+        for s, p in enumerate(procs):
+            ref = p.update(pts[k, s], cnt[k, s], hint=p.pose())
+            assert np.array_equal(bits(out[s]), bits(ref)), (k, s)
+    assert_same_maps(eng, procs, 3)
+    eng.close()
+
+
+def test_large_bounding_box_uses_global_fallback(hs, oracle):
+    """Scans whose bounding box exceeds the shared-memory cell map (here: a 2048^2 @0.01 m grid, box ~1000^2 cells)
+    take the ray-caster's global-marker path; results stay bit-exact."""
+    n, n_scans = 2, 6
+    sc, ranges, pts, cnt, truth = make_streams(hs, n, n_scans, seed0=1234, scale_to_map=100.0)
+    eng, procs = setup_pair(hs, oracle, n, size=2048, levels=2, res=0.01)
+    for k in range(n_scans):
+        out, _ = eng.update_batch(pts[k], cnt[k])
+        for s, p in enumerate(procs):
+            ref = p.update(pts[k, s], cnt[k, s], hint=p.pose())
+            assert np.array_equal(bits(out[s]), bits(ref)), (k, s)
+    assert_same_maps(eng, procs, 2)
+    eng.close()
+
+
+def test_upload_download_classify_roundtrip(hs):
+    with hs.Engine(0.05, 64, 64, (0.5, 0.5), 2, n_streams=2, max_points=8) as eng:
+        rng = np.random.default_rng(0)
+        for level, n in ((0, 64 * 64), (1, 32 * 32)):
+            cells = np.zeros(n, hs.CELL_DTYPE)
+            cells["logOddsVal"] = rng.normal(0, 1, n).astype(np.float32)
+            cells["logOddsVal"][::7] = 0.0
+            cells["updateIndex"] = rng.integers(-1, 100, n)
+            eng.upload_level(1, level, cells)
+            back = eng.download_level(1, level)
+            assert np.array_equal(back, cells)
+            occ = eng.classify_level(1, level)          # publishMap: isFree -> 0, isOccupied -> 100, else -1
+            v = cells["logOddsVal"]
+            assert np.array_equal(occ, np.where(v < 0, 0, np.where(v > 0, 100, -1)).astype(np.int8))
+            untouched = eng.download_level(0, level)
+            assert (untouched["logOddsVal"] == 0).all() and (untouched["updateIndex"] == -1).all()
+
+
+def test_match_only_and_pose_hypotheses(hs, oracle):
+    """hs_match_batch (no integration) and BASELINE config 4: 4096 pose hypotheses through getCompleteHessianDerivs."""
+    n_scans = 25
+    sc, ranges, pts, cnt, truth = make_streams(hs, 1, n_scans + 1, seed0=4096)
+    eng, procs = setup_pair(hs, oracle, 1)
+    p = procs[0]
+    for k in range(n_scans):
+        eng.update_batch(pts[k], cnt[k]); p.update(pts[k, 0], cnt[k, 0], hint=p.pose())
+    before = [eng.download_level(0, l) for l in range(3)]
+    hint = p.pose() + np.array([0.05, -0.03, 0.02], np.float32)
+    out, cov = eng.match_batch(pts[n_scans], cnt[n_scans], pose_hints=hint[None])
+    # oracle: matchData level by level (MapRepMultiMap::matchData)
+    ref = hint.astype(np.float32)
+    for level in (2, 1, 0):
+        scaled = (pts[n_scans, 0, :cnt[n_scans, 0]] * np.float32(1.0 / (1 << level))).astype(np.float32)
+        ref, rcov = p.match_level(level, ref, scaled, 5 if level == 0 else 3)
+    assert np.array_equal(bits(out[0]), bits(ref)) and np.array_equal(bits(cov[0]), bits(rcov))
+    for l in range(3):
+        assert np.array_equal(eng.download_level(0, l), before[l])         # match only: maps untouched
+    rng = np.random.default_rng(9)
+    base = p.world_to_map(0, p.pose())
+    hyp = (base[None] + rng.uniform(-1, 1, (4096, 3)) * np.array([20.0, 20.0, 0.5])).astype(np.float32)
+    scan = pts[n_scans, 0, :cnt[n_scans, 0]]
+    H, d = eng.hessian_derivs_batch(0, 0, hyp, scan)
+    Hc, dc = p.hessian_derivs_batch(0, hyp, scan)
+    assert np.array_equal(bits(H), bits(Hc)) and np.array_equal(bits(d), bits(dc))
+    eng.close()

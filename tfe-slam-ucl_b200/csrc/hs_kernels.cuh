@@ -515,9 +515,9 @@ struct HsBeamRec {
   unsigned char flags;         // bit0: dominant axis is x, bit1: step along a is +, bit2: step along b is +
 };
 
-// exact x / d for 0 <= x < 2^24, 0 < d < 2^24 (float reciprocal + one-step correction)
+// exact x / d for 0 <= x < 2^22, 0 < d < 2^22: approximate float quotient (MUFU.RCP, <= 2 ulp) + one-step correction
 __device__ __forceinline__ int hs_udiv_small(int x, int d, int& rem) {
-  int q = (int)((float)x * (1.0f / (float)d));
+  int q = (int)__fdividef((float)x, (float)d);
   int r = x - q * d;
   if (r < 0) { --q; r += d; }
   else if (r >= d) { ++q; r -= d; }
@@ -741,34 +741,33 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS) k_raycast(HsParams P, int 
   }
   __syncthreads();
 
-  // phase B2: updateSetFree exactly once per marked cell -- coalesced sweep of the bounding box,
-  // one warp per 32-cell row segment, 8 independent segments in flight per lane
+  // phase B2: updateSetFree exactly once per marked cell -- coalesced sweep of the bounding box: one warp per
+  // row, up to 8 independent 32-cell (128-byte aligned) segments in flight per lane
   {
     const int warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-    const int segs = ((x1 - x0) >> 5) + 1;         // 32-cell (128-byte aligned) segments per row
-    const int items = segs * bh;
-    for (int it0 = warp * 8; it0 < items; it0 += n_warps * 8) {
-      int g[8];
-      float v[8];
-      bool on[8];
+    const int segs = ((x1 - x0) >> 5) + 1;
+    for (int ry = warp; ry < bh; ry += n_warps) {
+      const int row = (y0 + ry) * W + x0 + lane;
+      const unsigned* frow = fmap + ry * pw;
+      for (int sg0 = 0; sg0 < segs; sg0 += 8) {
+        float v[8];
+        bool on[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        int it = it0 + u;
-        on[u] = false;
-        if (it < items) {
-          int sg;
-          int ry = hs_udiv_small(it, segs, sg);
-          g[u] = (y0 + ry) * W + x0 + (sg << 5) + lane;
-          if (use_map) on[u] = (fmap[ry * pw + sg] >> lane) & 1u;
-          else on[u] = (x0 + (sg << 5) + lane <= x1) && (__ldcg(idx + g[u]) == mark_free);
-          if (on[u]) v[u] = val[g[u]];
+        for (int u = 0; u < 8; ++u) {
+          const int sg = sg0 + u;
+          on[u] = false;
+          if (sg < segs) {
+            if (use_map) on[u] = (frow[sg] >> lane) & 1u;
+            else on[u] = (x0 + (sg << 5) + lane <= x1) && (__ldcg(idx + row + (sg << 5)) == mark_free);
+            if (on[u]) v[u] = val[row + (sg << 5)];
+          }
         }
-      }
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        if (on[u]) {
-          val[g[u]] = v[u] + f;
-          if (use_map) idx[g[u]] = mark_free;
+        for (int u = 0; u < 8; ++u) {
+          if (on[u]) {
+            val[row + ((sg0 + u) << 5)] = v[u] + f;
+            if (use_map) idx[row + ((sg0 + u) << 5)] = mark_free;
+          }
         }
       }
     }
