@@ -1,0 +1,86 @@
+"""Turns the ncu artefacts brought back in gpurun_out/ into the committed summaries under profiles/.
+
+    python profiles/summarize.py <tag> <launches.csv> <prof.ncu-rep> [<prof2.ncu-rep> ...]
+
+Writes profiles/<tag>_launches.csv (copy), profiles/<tag>_launches.md (per-kernel shares) and
+profiles/<tag>_<kernel>.md (key raw metrics, top stall reasons, hottest SASS lines) for every kernel found.
+"""
+import collections
+import csv
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "smsp__warps_active.avg.per_cycle_active", "smsp__warps_eligible.avg.per_cycle_active", "launch__registers_per_thread",
+        "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+        "launch__occupancy_limit_warps", "launch__waves_per_multiprocessor", "launch__grid_size", "launch__block_size",
+        "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "lts__t_sectors_srcunit_tex_op_read.sum",
+        "lts__t_sectors_srcunit_tex_op_write.sum", "lts__t_sectors_srcunit_tex_op_atom.sum", "lts__t_sectors_srcunit_tex_op_red.sum",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]
+
+
+def ncu_csv(rep, page, extra=()):
+    out = subprocess.run(["ncu", "-i", rep, "--page", page, "--csv"] + list(extra), capture_output=True, text=True).stdout
+    return list(csv.reader(out.splitlines()))
+
+
+def launches(tag, path):
+    shutil.copy(path, os.path.join(HERE, tag + "_launches.csv"))
+    rows = [r for r in csv.reader(open(path)) if len(r) > 10]
+    idx = {h: i for i, h in enumerate(rows[0])}
+    agg = collections.OrderedDict()
+    for r in rows[1:]:
+        agg.setdefault(r[idx["Kernel Name"]].split("(")[0], []).append(float(r[idx["Metric Value"]]) / 1e3)
+    hot = {k: v for k, v in agg.items() if k.startswith(("k_match", "void k_match", "k_raycast", "k_scan_to_points"))}
+    tot = sum(sum(v) for v in hot.values())
+    with open(os.path.join(HERE, tag + "_launches.md"), "w") as f:
+        f.write("# %s: every launch with its device time (ncu --metrics gpu__time_duration.sum --clock-control none)\n\n" % tag)
+        f.write("Times are cold-cache and serialised by the profiler: compare SHARES with bench.py's CUDA-event shares, not absolutes.\n\n")
+        f.write("| kernel | launches | avg us | min us | max us | share of hot-path time |\n|---|---|---|---|---|---|\n")
+        for k, v in agg.items():
+            f.write("| %s | %d | %.1f | %.1f | %.1f | %s |\n" % (k, len(v), sum(v) / len(v), min(v), max(v), "%.3f" % (sum(v) / tot) if k in hot else "-"))
+
+
+def kernels(tag, rep):
+    raw = ncu_csv(rep, "raw")
+    hdr, units = raw[0], raw[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    seen = set()
+    for r in raw[2:]:
+        name = r[idx["Kernel Name"]].split("(")[0].replace("void ", "").replace("<", "_").replace(">", "")
+        if name in seen:
+            continue
+        seen.add(name)
+        with open(os.path.join(HERE, "%s_%s.md" % (tag, name)), "w") as f:
+            f.write("# %s -- %s (ncu --set full --clock-control none --import-source on, one launch)\n\n" % (tag, r[idx["Kernel Name"]]))
+            f.write("| metric | value | unit |\n|---|---|---|\n")
+            for k in KEYS:
+                if k in idx and r[idx[k]] not in ("", "n/a"):
+                    f.write("| %s | %s | %s |\n" % (k, r[idx[k]], units[idx[k]]))
+            stalls = sorted([(float(r[idx[h]]), h) for h in hdr if "issue_stalled" in h and h.endswith("per_issue_active.ratio") and r[idx[h]] not in ("", "n/a")], reverse=True)[:8]
+            f.write("\nTop warp-stall reasons (warps stalled per issue-active cycle):\n\n")
+            for v, h in stalls:
+                f.write("* %.2f  %s\n" % (v, h.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", "")))
+            src = ncu_csv(rep, "source", ["--kernel-name", "regex:" + r[idx["Kernel Name"]].split("(")[0].replace("void ", "").split("<")[0], "--launch-count", "1"])
+            if len(src) > 2:
+                sh = src[1]
+                si = {h: i for i, h in enumerate(sh)}
+                data = [x for x in src[2:] if len(x) > si["Instructions Executed"] and x[si["# Samples"]].isdigit()]
+                tot = sum(int(x[si["# Samples"]]) for x in data) or 1
+                f.write("\nHottest SASS instructions (stall samples, %d total):\n\n```\n" % tot)
+                for x in sorted(data, key=lambda x: -int(x[si["# Samples"]]))[:20]:
+                    f.write("%5.1f%%  exec %10s  %s\n" % (100.0 * int(x[si["# Samples"]]) / tot, x[si["Instructions Executed"]], x[si["Source"]].strip()[:100]))
+                f.write("```\n")
+
+
+if __name__ == "__main__":
+    tag = sys.argv[1]
+    launches(tag, sys.argv[2])
+    for rep in sys.argv[3:]:
+        kernels(tag, rep)
