@@ -458,26 +458,23 @@ __global__ void __launch_bounds__(HS_MATCH_THREADS) k_hessian_derivs(HsParams P,
 //   A1  per beam: end cell, Bresenham parameters -> beam record; bounding box of the scan
 //   A2  per beam: end cell -> shared hash table (cell -> smallest beam index io, via atomicMin) and the
 //       end-cell bit plane of the CTA's cell map
-//   B1  free cells of all beams. bresenham2D's state after t steps has the closed form
-//           cell(t) = k0 + t*off_a + floor((abs_da/2 + t*abs_db) / abs_da) * off_b,   t = 0 .. abs_da-1,
-//       so the free cells of a beam are independent work items: a group of G adjacent lanes (G = 32, 16, 8 on
-//       levels 0, 1, 2+) owns one beam at a time, lane j takes t = j, j+G, ... and advances the error term G
-//       steps at once. Marks go to a bit-per-cell plane of the bounding box (shared-memory atomicOr, skipped when
-//       the bit is already set); the ~49 k scattered cell visits of a scan never reach L2/HBM. A free cell that is some beam's end cell
-//       (end-cell plane) looks io up in the hash table and, if this beam < io, sets the entry's
-//       "free came first" flag.
+//   B1  free cells of all beams: one thread walks one beam with the reference's bresenham2D recurrence
+//       (OccGridMapBase.h:243-260) -- but in a 2-bit-per-cell map of the bounding box held in SHARED memory
+//       (free bit set with a shared-memory atomicOr, skipped when already set): the ~49 k scattered cell visits of a
+//       scan never reach L2/HBM. A free cell that is some beam's end cell (end bit) looks io up in the hash
+//       table and, if this beam < io, sets the entry's "free came first" flag.
 //   B2  coalesced sweep of the box: free bit set -> idx = markFree, val += f  (exactly once per cell)
 //   C   end points: the beam that owns io applies undo-free / occupied to val and stores markOcc.
-// If the bounding box does not fit the cell map (HS_PLANE_BYTES per plane) B1/B2 fall back to marking in the
+// If the bounding box does not fit the cell map (HS_MAP_CELLS cells) B1/B2 fall back to marking in the
 // global marker plane: idx = markFree by plain store (idempotent), then the sweep applies f where
 // idx == markFree (only this scan can have written that value); end cells are recognised by a hash probe.
 // No scratch value is ever stored in the grids, and no global atomic is used. A beam's own trace never
 // contains its own end point (bresenham2D visits abs_da cells from the start).
 
 #define HS_HASH_EMPTY (-1)
-#define HS_PLANE_BYTES 24576              // one bit plane of the shared-memory cell map (196608 cells, e.g. 443^2)
-#define HS_MAP_BYTES (2 * HS_PLANE_BYTES)  // plane 0: crossed by a free trace, plane 1: some beam's end cell
-#define HS_RAYCAST_THREADS 256
+#define HS_MAP_BYTES 49152                 // shared-memory cell map: 2 bits per cell, 16 cells per 32-bit word
+#define HS_MAP_CELLS (HS_MAP_BYTES * 4)    // low half-word: crossed by a free trace; high half-word: some beam's end cell
+#define HS_RAYCAST_THREADS 384
 
 struct HsBeam {
   int valid;            // begin != end and both inside the grid
@@ -510,9 +507,8 @@ __device__ __forceinline__ HsBeam hs_make_beam(const HsLevel& L, int bx, int by,
 // Beam record kept in shared memory between the phases (one per scan point), 12 bytes.
 struct HsBeamRec {
   int kend;                    // end cell offset in the grid
-  unsigned short da, db, rg;   // abs_da (0 marks a dropped beam), abs_db, (G*abs_db) % abs_da
-  unsigned char qg;            // (G*abs_db) / abs_da: the error-term advance of G steps at once
-  unsigned char flags;         // bit0: dominant axis is x, bit1: step along a is +, bit2: step along b is +
+  unsigned short da, db;       // abs_da (0 marks a dropped beam), abs_db
+  unsigned int flags;          // bit0: dominant axis is x, bit1: step along a is +, bit2: step along b is +
 };
 
 // exact x / d for 0 <= x < 2^22, 0 < d < 2^22: approximate float quotient (MUFU.RCP, <= 2 ulp) + one-step correction
@@ -546,8 +542,7 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS) k_raycast(HsParams P, int 
                                                                 const float2* __restrict__ origos, int log2_hash) {
   extern __shared__ __align__(16) unsigned char hs_smem[];
   const int hash_size = 1 << log2_hash, hash_mask = hash_size - 1;
-  unsigned* fmap = reinterpret_cast<unsigned*>(hs_smem);                   // free-trace bits
-  unsigned* emap = reinterpret_cast<unsigned*>(hs_smem + HS_PLANE_BYTES);  // end-cell bits
+  unsigned* cmap = reinterpret_cast<unsigned*>(hs_smem);                   // 16 cells per word: free bits | end bits << 16
   int* hkeys = reinterpret_cast<int*>(hs_smem + HS_MAP_BYTES);             // end cell (grid offset) or EMPTY
   int* hvals = hkeys + hash_size;                                          // (io << 1) | free-came-first flag
   HsBeamRec* beams = reinterpret_cast<HsBeamRec*>(hvals + hash_size);
@@ -591,7 +586,6 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS) k_raycast(HsParams P, int 
   const int bx = (int)(((cs * ox + (-sn) * oy) + mpx) + 0.5f);  // Vector2i(float, float): truncation (OccGridMapBase.h:137)
   const int by = (int)(((sn * ox + cs * oy) + mpy) + 0.5f);
   const float pf = L.pt_factor;
-  const int G = level == 0 ? 32 : (level == 1 ? 16 : 8);
   const int lane = threadIdx.x & 31;
 
   // clear the cell map and the hash table (independent of everything else), reset the box
@@ -610,14 +604,11 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS) k_raycast(HsParams P, int 
     float2 p = pts[i];
     HsBeam b = hs_make_beam(L, bx, by, mpx, mpy, sn, cs, p.x * pf, p.y * pf);
     HsBeamRec r;
-    r.kend = b.kend; r.da = 0; r.db = (unsigned short)b.abs_db; r.rg = 0; r.qg = 0;
-    r.flags = (unsigned char)((b.a_is_x ? 1 : 0) | (b.sa > 0 ? 2 : 0) | (b.sb > 0 ? 4 : 0));
+    r.kend = b.kend; r.da = 0; r.db = (unsigned short)b.abs_db;
+    r.flags = (unsigned)((b.a_is_x ? 1 : 0) | (b.sa > 0 ? 2 : 0) | (b.sb > 0 ? 4 : 0));
     if (b.valid) {
       visits += b.abs_da + 1u;
       r.da = (unsigned short)b.abs_da;
-      int rg;
-      r.qg = (unsigned char)hs_udiv_small(G * (int)b.abs_db, (int)b.abs_da, rg);
-      r.rg = (unsigned short)rg;
       xmin = min(xmin, b.ex); xmax = max(xmax, b.ex); ymin = min(ymin, b.ey); ymax = max(ymax, b.ey);
     }
     beams[i] = r;
@@ -633,13 +624,13 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS) k_raycast(HsParams P, int 
   __syncthreads();
   if (s_box[2] < s_box[0]) return;  // no valid beam (uniform for the CTA)
 
-  // geometry of the cell map: rows of pw 32-cell words starting at a 32-aligned x0; pw odd so that a vertical
-  // run of cells spreads over the shared-memory banks
+  // geometry of the cell map: rows of `pitch` cells starting at a 32-aligned x0; the row pitch in words is odd so
+  // that a vertical run of cells spreads over the shared-memory banks
   const int x0 = s_box[0] & ~31, y0 = s_box[1], x1 = s_box[2], y1 = s_box[3];
   const int bh = y1 - y0 + 1;
-  const int pw = (((x1 - x0) >> 5) + 1) | 1;
-  const int pitch = pw << 5;  // cells per map row
-  const bool use_map = (long long)pw * bh * 4 <= HS_PLANE_BYTES;
+  const int pw = (((x1 - x0) >> 4) + 1) | 1;   // 16-cell words per map row
+  const int pitch = pw << 4;                   // cells per map row
+  const bool use_map = (long long)pitch * bh <= HS_MAP_CELLS;
 
   // phase A2: end point ownership -- io = smallest beam index per end cell
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -655,87 +646,51 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS) k_raycast(HsParams P, int 
     if (use_map) {
       int ey = r.kend / W, ex = r.kend - ey * W;
       int kb = (ey - y0) * pitch + (ex - x0);
-      atomicOr(&emap[kb >> 5], 1u << (kb & 31));
+      atomicOr(&cmap[kb >> 4], 0x10000u << (kb & 15));
     }
   }
   __syncthreads();
 
-  // phase B1: free cells (bresenham2D, OccGridMapBase.h:243-260), G lanes per beam
+  // phase B1: free cells -- one thread per beam, the reference's bresenham2D recurrence (OccGridMapBase.h:243-260)
   {
-    const int j = threadIdx.x & (G - 1);
-    const int group = threadIdx.x / G, n_groups = blockDim.x / G;
     const int row_step = use_map ? pitch : W;                       // address step of one cell in y
     const int k0 = use_map ? (by - y0) * pitch + (bx - x0) : by * W + bx;
-    for (int i0 = 0; i0 < n; i0 += n_groups) {                       // same trip count for every thread of the CTA
-      const int i = i0 + group;
-      int da = 0, db = 0, rg = 0, off_b = 0, kstep = 0, k = 0, err = 0;
-      if (i < n) {
-        const HsBeamRec r = beams[i];
-        if (j < (int)r.da) {
-          da = r.da; db = r.db; rg = r.rg;
-          const int sa = (r.flags & 2) ? 1 : -1, sb = (r.flags & 4) ? 1 : -1;
-          const int off_a = (r.flags & 1) ? sa : sa * row_step;
-          off_b = (r.flags & 1) ? sb * row_step : sb;
-          int q = hs_udiv_small((da >> 1) + j * db, da, err);
-          k = k0 + j * off_a + q * off_b;
-          kstep = G * off_a + (int)r.qg * off_b;
-        }
-      }
-      int t = j;
-      if (use_map) {
-        for (;;) {
-          const bool valid = t < da;
-          const unsigned bal = __ballot_sync(0xffffffffu, valid);
-          if (bal == 0u) break;
-          if (valid) {
-            const int widx = k >> 5;
-            const unsigned bit = 1u << (k & 31);
-            const bool is_end = (emap[widx] & bit) != 0u;
-            if (is_end) {
-              // the free trace of beam i crosses a cell that is some beam's end point
-              int xx;
-              int yy = hs_udiv_small(k, pitch, xx);
-              int h = hs_hash_find(hkeys, hash_mask, log2_hash, (yy + y0) * W + (xx + x0));
-              if (h >= 0) {
-                int hv = hvals[h];
-                if (i < (hv >> 1) && !(hv & 1)) atomicOr(&hvals[h], 1);
-              }
-            } else if ((fmap[widx] & bit) == 0u) {
-              atomicOr(&fmap[widx], bit);   // lanes of one warp on the same word serialise in the LSU (~1 cycle each)
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const HsBeamRec r = beams[i];
+      const int da = r.da, db = r.db;
+      if (da == 0) continue;
+      const int sa = (r.flags & 2) ? 1 : -1, sb = (r.flags & 4) ? 1 : -1;
+      const int off_a = (r.flags & 1) ? sa : sa * row_step;
+      const int off_b = (r.flags & 1) ? sb * row_step : sb;
+      int k = k0, err = da >> 1;
+      for (int t = 0; t < da; ++t) {
+        if (use_map) {
+          const unsigned word = cmap[k >> 4];
+          const unsigned sh = (unsigned)k & 15u;
+          if ((word >> (16u + sh)) & 1u) {
+            // the free trace of beam i crosses a cell that is some beam's end point
+            int xx;
+            int yy = hs_udiv_small(k, pitch, xx);
+            int h = hs_hash_find(hkeys, hash_mask, log2_hash, (yy + y0) * W + (xx + x0));
+            if (h >= 0) {
+              int hv = hvals[h];
+              if (i < (hv >> 1) && !(hv & 1)) atomicOr(&hvals[h], 1);
             }
-            t += G;
-            k += kstep;
-            err += rg;
-            if (err >= da) { k += off_b; err -= da; }
+          } else if (!((word >> sh) & 1u)) {
+            atomicOr(&cmap[k >> 4], 1u << sh);
+          }
+        } else {
+          int h = hs_hash_find(hkeys, hash_mask, log2_hash, k);
+          if (h >= 0) {                 // end cell: only the "free came first" flag matters
+            int hv = hvals[h];
+            if (i < (hv >> 1) && !(hv & 1)) atomicOr(&hvals[h], 1);
+          } else if (idx[k] < mark_free) {  // may be served by L1: a stale "not yet marked" only repeats an idempotent store
+            idx[k] = mark_free;
           }
         }
-      } else {
-        while (t < da) {
-          int kk[4], w[4];
-          int c = 0;
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            w[u] = INT_MAX;
-            if (t < da) {
-              kk[u] = k;
-              c = u + 1;
-              int h = hs_hash_find(hkeys, hash_mask, log2_hash, k);
-              if (h >= 0) {                 // end cell: only the "free came first" flag matters
-                int hv = hvals[h];
-                if (i < (hv >> 1) && !(hv & 1)) atomicOr(&hvals[h], 1);
-              } else {
-                w[u] = idx[k];              // may be served by L1: a stale "not yet marked" only repeats an idempotent store
-              }
-              t += G;
-              k += kstep;
-              err += rg;
-              if (err >= da) { k += off_b; err -= da; }
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-            if (u < c && w[u] < mark_free) idx[kk[u]] = mark_free;
-        }
+        k += off_a;
+        err += db;
+        if (err >= da) { k += off_b; err -= da; }
       }
     }
   }
@@ -748,7 +703,7 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS) k_raycast(HsParams P, int 
     const int segs = ((x1 - x0) >> 5) + 1;
     for (int ry = warp; ry < bh; ry += n_warps) {
       const int row = (y0 + ry) * W + x0 + lane;
-      const unsigned* frow = fmap + ry * pw;
+      const unsigned* mrow = cmap + ry * pw + (lane >> 4);
       for (int sg0 = 0; sg0 < segs; sg0 += 8) {
         float v[8];
         bool on[8];
@@ -757,8 +712,9 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS) k_raycast(HsParams P, int 
           const int sg = sg0 + u;
           on[u] = false;
           if (sg < segs) {
-            if (use_map) on[u] = (frow[sg] >> lane) & 1u;
-            else on[u] = (x0 + (sg << 5) + lane <= x1) && (__ldcg(idx + row + (sg << 5)) == mark_free);
+            const bool inside = x0 + (sg << 5) + lane <= x1;   // the last segment may stick out of the box / map row
+            if (use_map) on[u] = inside && ((mrow[sg * 2] >> (lane & 15)) & 1u);
+            else on[u] = inside && (__ldcg(idx + row + (sg << 5)) == mark_free);
             if (on[u]) v[u] = val[row + (sg << 5)];
           }
         }
