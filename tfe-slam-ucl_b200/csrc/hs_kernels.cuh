@@ -663,8 +663,8 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS) k_raycast(HsParams P, int 
       const int off_a = (r.flags & 1) ? sa : sa * row_step;
       const int off_b = (r.flags & 1) ? sb * row_step : sb;
       int k = k0, err = da >> 1;
-      for (int t = 0; t < da; ++t) {
-        if (use_map) {
+      if (use_map) {
+        for (int t = 0; t < da; ++t) {
           const unsigned word = cmap[k >> 4];
           const unsigned sh = (unsigned)k & 15u;
           if ((word >> (16u + sh)) & 1u) {
@@ -679,7 +679,12 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS) k_raycast(HsParams P, int 
           } else if (!((word >> sh) & 1u)) {
             atomicOr(&cmap[k >> 4], 1u << sh);
           }
-        } else {
+          k += off_a;
+          err += db;
+          if (err >= da) { k += off_b; err -= da; }
+        }
+      } else {
+        for (int t = 0; t < da; ++t) {
           int h = hs_hash_find(hkeys, hash_mask, log2_hash, k);
           if (h >= 0) {                 // end cell: only the "free came first" flag matters
             int hv = hvals[h];
@@ -687,28 +692,65 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS) k_raycast(HsParams P, int 
           } else if (idx[k] < mark_free) {  // may be served by L1: a stale "not yet marked" only repeats an idempotent store
             idx[k] = mark_free;
           }
+          k += off_a;
+          err += db;
+          if (err >= da) { k += off_b; err -= da; }
         }
-        k += off_a;
-        err += db;
-        if (err >= da) { k += off_b; err -= da; }
       }
     }
   }
   __syncthreads();
 
-  // phase B2: updateSetFree exactly once per marked cell -- coalesced sweep of the bounding box: one warp per
-  // row, up to 8 independent 32-cell (128-byte aligned) segments in flight per lane
-  {
+  // phase B2: updateSetFree exactly once per marked cell -- coalesced sweep of the bounding box, one warp per row.
+  const bool vec_ok = use_map && ((W & 3) == 0) && ((reinterpret_cast<uintptr_t>(val) & 15) == 0);
+  if (vec_ok) {
+    // fast path: a lane owns 4 consecutive cells (one float4), a warp covers 128 cells per step. Unmarked
+    // components are written back unchanged, hence the barrier before phase C touches the end cells.
+    const int warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const int chunks = ((x1 - x0) >> 7) + 1;
+    for (int ry = warp; ry < bh; ry += n_warps) {
+      const int row = (y0 + ry) * W + x0 + (lane << 2);
+      const unsigned* mrow = cmap + ry * pw + (lane >> 2);
+      const unsigned sh = (unsigned)(lane & 3) << 2;
+      for (int c0 = 0; c0 < chunks; c0 += 2) {
+        unsigned bits[2];
+        float4 v[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int c = c0 + u;
+          bits[u] = 0u;
+          if (c < chunks && x0 + (c << 7) + (lane << 2) <= x1) {
+            bits[u] = (mrow[c << 3] >> sh) & 0xFu;
+            if (bits[u]) v[u] = *reinterpret_cast<const float4*>(val + row + (c << 7));
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          if (bits[u]) {
+            const int g = row + ((c0 + u) << 7);
+            float4 w = v[u];
+            if (bits[u] & 1u) { w.x = w.x + f; idx[g] = mark_free; }
+            if (bits[u] & 2u) { w.y = w.y + f; idx[g + 1] = mark_free; }
+            if (bits[u] & 4u) { w.z = w.z + f; idx[g + 2] = mark_free; }
+            if (bits[u] & 8u) { w.w = w.w + f; idx[g + 3] = mark_free; }
+            *reinterpret_cast<float4*>(val + g) = w;
+          }
+        }
+      }
+    }
+    __syncthreads();
+  } else {
+    // generic path (any grid width, and the global-marker fallback): a lane owns one cell per 32-cell segment
     const int warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
     const int segs = ((x1 - x0) >> 5) + 1;
     for (int ry = warp; ry < bh; ry += n_warps) {
       const int row = (y0 + ry) * W + x0 + lane;
       const unsigned* mrow = cmap + ry * pw + (lane >> 4);
-      for (int sg0 = 0; sg0 < segs; sg0 += 8) {
-        float v[8];
-        bool on[8];
+      for (int sg0 = 0; sg0 < segs; sg0 += 4) {
+        float v[4];
+        bool on[4];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < 4; ++u) {
           const int sg = sg0 + u;
           on[u] = false;
           if (sg < segs) {
@@ -719,7 +761,7 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS) k_raycast(HsParams P, int 
           }
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < 4; ++u) {
           if (on[u]) {
             val[row + ((sg0 + u) << 5)] = v[u] + f;
             if (use_map) idx[row + ((sg0 + u) << 5)] = mark_free;
