@@ -251,8 +251,8 @@ int hs_create(const hs_config* cfg, hs_engine** out) {
   {
     int smem = cfg->max_points * HS_NPROD * (int)sizeof(float);  // k_match's per-CTA product buffer
     if (smem > 48 * 1024) {
-      cudaError_t e1 = cudaFuncSetAttribute(k_match<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-      cudaError_t e2 = cudaFuncSetAttribute(k_match<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      cudaError_t e1 = cudaFuncSetAttribute(k_match<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      cudaError_t e2 = cudaFuncSetAttribute(k_match<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
       if (e1 != cudaSuccess || e2 != cudaSuccess) {
         hs_destroy(e);
         return (int)(e1 != cudaSuccess ? e1 : e2);
@@ -390,12 +390,22 @@ static int run_update_device(hs_engine* e, int n, const int32_t* ids, const floa
   const size_t smem = (size_t)e->P.max_points * HS_NPROD * sizeof(float);
   {
     ProfScope ps(e, HS_K_MATCH);
-    if (e->P.strict)
-      k_match<true><<<n, HS_MATCH_THREADS, smem, e->stream>>>(e->P, n, ids, (const float2*)points, counts,
-                                                             (const float2*)origos, hints, flags, mode);
-    else
-      k_match<false><<<n, HS_MATCH_THREADS, smem, e->stream>>>(e->P, n, ids, (const float2*)points, counts,
-                                                              (const float2*)origos, hints, flags, mode);
+    const int threads = HS_MATCH_THREADS;
+    int ppt = (e->P.max_points + threads - 1) / threads;   // register-resident points (+ cell caches) per thread
+    ppt = ppt <= 2 ? 2 : (ppt <= 3 ? 3 : (ppt <= 6 ? 6 : 0));
+#define HS_LAUNCH_MATCH(STRICT_, PPT_)                                                               \
+  k_match<STRICT_, PPT_><<<n, threads, smem, e->stream>>>(e->P, n, ids, (const float2*)points, counts, \
+                                                        (const float2*)origos, hints, flags, mode)
+#define HS_LAUNCH_MATCH_S(STRICT_)                                    \
+  do {                                                                \
+    if (ppt == 2) HS_LAUNCH_MATCH(STRICT_, 2);                        \
+    else if (ppt == 3) HS_LAUNCH_MATCH(STRICT_, 3);                   \
+    else if (ppt == 6) HS_LAUNCH_MATCH(STRICT_, 6);                   \
+    else HS_LAUNCH_MATCH(STRICT_, 0);                                 \
+  } while (0)
+    if (e->P.strict) HS_LAUNCH_MATCH_S(true); else HS_LAUNCH_MATCH_S(false);
+#undef HS_LAUNCH_MATCH_S
+#undef HS_LAUNCH_MATCH
   }
   HS_LAUNCHED(e);
   if (mode == 0) {

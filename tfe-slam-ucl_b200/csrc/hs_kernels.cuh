@@ -144,9 +144,18 @@ struct HsAcc {  // dTr[3] and the upper triangle of H
   float d0, d1, d2, h00, h11, h22, h01, h02, h12;
 };
 
+// The four cell probabilities around a point, remembered between evaluations: Gauss-Newton steps on one level are
+// mostly sub-cell, so the same 2x2 cell block is hit again and its log-odds -> probability conversions (4 double
+// precision expf + 4 divisions) and gathers can be skipped. Exactly the same values either way.
+struct HsCellCache {
+  int key;          // cell offset of the block's first cell on the current level, -1 = empty
+  float p0, p1, p2, p3;
+};
+
 // Per-point terms: (gx, gy, rot, funVal). Out-of-bounds points contribute zeros like the reference.
+template <bool CACHED>
 __device__ __forceinline__ void hs_point_terms(const float* __restrict__ val, const HsLevel& L, float ex, float ey,
-                                               float sn, float cs, float px, float py,
+                                               float sn, float cs, float px, float py, HsCellCache& cc,
                                                float& gx, float& gy, float& rot, float& fun_val) {
   float qx = (cs * px + (-sn) * py) + ex;  // Affine2f * v = linear*v + translation
   float qy = (sn * px + cs * py) + ey;
@@ -156,9 +165,16 @@ __device__ __forceinline__ void hs_point_terms(const float* __restrict__ val, co
   if (qx >= 0.0f && qx <= L.limx && qy >= 0.0f && qy <= L.limy) {  // !pointOutOfMapBounds
     int ix = (int)qx, iy = (int)qy;
     float fx = qx - (float)ix, fy = qy - (float)iy;
-    const float* p = val + (size_t)iy * L.sx + ix;
-    float v0 = __ldg(p), v1 = __ldg(p + 1), v2 = __ldg(p + L.sx), v3 = __ldg(p + L.sx + 1);
-    float i0 = hs_probability(v0), i1 = hs_probability(v1), i2 = hs_probability(v2), i3 = hs_probability(v3);
+    const int k = iy * L.sx + ix;
+    float i0, i1, i2, i3;
+    if (CACHED && k == cc.key) {
+      i0 = cc.p0; i1 = cc.p1; i2 = cc.p2; i3 = cc.p3;
+    } else {
+      const float* p = val + k;
+      float v0 = __ldg(p), v1 = __ldg(p + 1), v2 = __ldg(p + L.sx), v3 = __ldg(p + L.sx + 1);
+      i0 = hs_probability(v0); i1 = hs_probability(v1); i2 = hs_probability(v2); i3 = hs_probability(v3);
+      if (CACHED) { cc.key = k; cc.p0 = i0; cc.p1 = i1; cc.p2 = i2; cc.p3 = i3; }
+    }
     float dx1 = i0 - i1, dx2 = i2 - i3;
     float dy1 = i0 - i2, dy2 = i1 - i3;
     float x_inv = 1.0f - fx, y_inv = 1.0f - fy;
@@ -195,23 +211,42 @@ __device__ __forceinline__ void hs_acc_add(HsAcc& a, float gx, float gy, float r
 // Must be called by all threads of the CTA; contains two __syncthreads. Only warp 0's return value is defined.
 #define HS_NPROD 9
 
-template <bool STRICT>
+__device__ __forceinline__ void hs_store_products(float* __restrict__ q, float gx, float gy, float rot, float fv) {
+  q[0] = gx * fv;   // dTr[0]
+  q[1] = gy * fv;   // dTr[1]
+  q[2] = rot * fv;  // dTr[2]
+  q[3] = gx * gx;   // H(0,0)
+  q[4] = gy * gy;   // H(1,1)
+  q[5] = rot * rot; // H(2,2)
+  q[6] = gx * gy;   // H(0,1)
+  q[7] = gx * rot;  // H(0,2)
+  q[8] = gy * rot;  // H(1,2)
+}
+
+// PPT > 0: the thread's points (i = tid + j*blockDim, j < PPT) are held in registers by the caller (they are the
+// same for all evaluations of a scan); PPT == 0: read them from `pts` (any n).
+template <bool STRICT, int PPT>
 __device__ __forceinline__ HsAcc hs_eval_cta(const float* __restrict__ val, const HsLevel& L, float ex, float ey, float sn, float cs,
-                                             const float2* __restrict__ pts, int n, float pt_factor, float* __restrict__ prod) {
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    float2 p = pts[i];
-    float gx, gy, rot, fv;
-    hs_point_terms(val, L, ex, ey, sn, cs, p.x * pt_factor, p.y * pt_factor, gx, gy, rot, fv);
-    float* q = prod + i * HS_NPROD;
-    q[0] = gx * fv;   // dTr[0]
-    q[1] = gy * fv;   // dTr[1]
-    q[2] = rot * fv;  // dTr[2]
-    q[3] = gx * gx;   // H(0,0)
-    q[4] = gy * gy;   // H(1,1)
-    q[5] = rot * rot; // H(2,2)
-    q[6] = gx * gy;   // H(0,1)
-    q[7] = gx * rot;  // H(0,2)
-    q[8] = gy * rot;  // H(1,2)
+                                             const float2* __restrict__ pts, const float2* preg, HsCellCache* cache, int n,
+                                             float pt_factor, float* __restrict__ prod) {
+  if (PPT > 0) {
+#pragma unroll
+    for (int j = 0; j < (PPT > 0 ? PPT : 1); ++j) {
+      const int i = threadIdx.x + j * blockDim.x;
+      if (i < n) {
+        float gx, gy, rot, fv;
+        hs_point_terms<true>(val, L, ex, ey, sn, cs, preg[j].x * pt_factor, preg[j].y * pt_factor, cache[j], gx, gy, rot, fv);
+        hs_store_products(prod + i * HS_NPROD, gx, gy, rot, fv);
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      float2 p = pts[i];
+      float gx, gy, rot, fv;
+      HsCellCache none;
+      hs_point_terms<false>(val, L, ex, ey, sn, cs, p.x * pt_factor, p.y * pt_factor, none, gx, gy, rot, fv);
+      hs_store_products(prod + i * HS_NPROD, gx, gy, rot, fv);
+    }
   }
   __syncthreads();
   HsAcc a = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -300,9 +335,9 @@ __device__ __forceinline__ bool hs_gauss_newton_step(const HsAcc& a, float& ex, 
 // (sums, 3x3 solve, sin/cos of the new angle); the other warps only help with the per-point gathers.
 // mode: 0 = update (match + gate), 1 = match only (no gate, no integration).
 // dynamic shared memory: max_points * 9 floats.
-#define HS_MATCH_THREADS 128
+#define HS_MATCH_THREADS 128   // measured on B200 at 1024 streams: 64 -> 160 us, 96 -> 122, 128 -> 109, 192/256 -> 143 per launch
 
-template <bool STRICT>
+template <bool STRICT, int PPT>
 __global__ void __launch_bounds__(HS_MATCH_THREADS) k_match(HsParams P, int n_slots, const int32_t* __restrict__ stream_ids,
                                                             const float2* __restrict__ points, const int32_t* __restrict__ counts,
                                                             const float2* __restrict__ origos, const float* __restrict__ hints,
@@ -336,10 +371,21 @@ __global__ void __launch_bounds__(HS_MATCH_THREADS) k_match(HsParams P, int n_sl
       const float* val_s = P.val + (size_t)s * P.cells_per_stream;
       HsAcc a = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       unsigned clamps = 0;
+      float2 preg[PPT > 0 ? PPT : 1];
+      HsCellCache cache[PPT > 0 ? PPT : 1];
+      if (PPT > 0) {
+#pragma unroll
+        for (int j = 0; j < (PPT > 0 ? PPT : 1); ++j) {
+          const int i = tid + j * blockDim.x;
+          preg[j] = i < n ? pts[i] : make_float2(0.f, 0.f);
+        }
+      }
       for (int level = P.n_levels - 1; level >= 0; --level) {
         const HsLevel& L = P.lv[level];
         const float* val = val_s + L.cell_offset;
         float ex = 0.f, ey = 0.f, eth = wth;
+#pragma unroll
+        for (int j = 0; j < (PPT > 0 ? PPT : 1); ++j) cache[j].key = -1;   // a new level is a new grid
         if (tid < 32) {
           hs_world_to_map(L, wx, wy, ex, ey);
           if (tid == 0) { s_est[0] = ex; s_est[1] = ey; s_est[2] = eth; s_est[3] = hs_sinf(eth); s_est[4] = hs_cosf(eth); }
@@ -347,7 +393,7 @@ __global__ void __launch_bounds__(HS_MATCH_THREADS) k_match(HsParams P, int n_sl
         __syncthreads();
         for (int it = 0; it <= L.max_iter; ++it) {  // 1 + maxIterations evaluations, no early exit
           const float cex = s_est[0], cey = s_est[1], csn = s_est[3], ccs = s_est[4];
-          a = hs_eval_cta<STRICT>(val, L, cex, cey, csn, ccs, pts, n, L.pt_factor, hs_prod);
+          a = hs_eval_cta<STRICT, PPT>(val, L, cex, cey, csn, ccs, pts, preg, cache, n, L.pt_factor, hs_prod);
           if (tid < 32) {
             clamps += hs_gauss_newton_step(a, ex, ey, eth) ? 1u : 0u;
             if (tid == 0) { s_est[0] = ex; s_est[1] = ey; s_est[2] = eth; s_est[3] = hs_sinf(eth); s_est[4] = hs_cosf(eth); }
@@ -430,7 +476,7 @@ __global__ void __launch_bounds__(HS_MATCH_THREADS) k_hessian_derivs(HsParams P,
   const HsLevel& L = P.lv[level];
   const float* val = P.val + (size_t)stream * P.cells_per_stream + L.cell_offset;
   const float th = poses_map[3 * k + 2];
-  HsAcc a = hs_eval_cta<STRICT>(val, L, poses_map[3 * k], poses_map[3 * k + 1], hs_sinf(th), hs_cosf(th), pts, n_pts, 1.0f, hs_prod);
+  HsAcc a = hs_eval_cta<STRICT, 0>(val, L, poses_map[3 * k], poses_map[3 * k + 1], hs_sinf(th), hs_cosf(th), pts, nullptr, nullptr, n_pts, 1.0f, hs_prod);
   if (threadIdx.x == 0) {
     float* h = H9 + 9 * (size_t)k;
     h[0] = a.h00; h[1] = a.h01; h[2] = a.h02;
