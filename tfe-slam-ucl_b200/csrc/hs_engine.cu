@@ -93,7 +93,7 @@ static int raycast_log2_hash(int max_points) {
   return l;
 }
 static size_t raycast_smem_for(int max_points) {
-  return (size_t)HS_MAP_BYTES + 2 * sizeof(int) * ((size_t)1 << raycast_log2_hash(max_points)) + (size_t)max_points * sizeof(HsBeamRec);
+  return (size_t)HS_MAP_BYTES + 2 * sizeof(int) * ((size_t)1 << raycast_log2_hash(max_points)) + (size_t)max_points * sizeof(HsBeamRec) + (size_t)max_points * sizeof(unsigned short) + 16;
 }
 static size_t raycast_smem(const hs_engine* e) { return raycast_smem_for(e->P.max_points); }
 static int warp_grid(int n_warps, int threads) { return (n_warps * 32 + threads - 1) / threads; }

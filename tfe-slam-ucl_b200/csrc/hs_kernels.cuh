@@ -503,7 +503,10 @@ __global__ void __launch_bounds__(HS_MATCH_THREADS) k_hessian_derivs(HsParams P,
 // coalesced updates:
 //   A1  per beam: end cell, Bresenham parameters -> beam record; bounding box of the scan
 //   A2  per beam: end cell -> shared hash table (cell -> smallest beam index io, via atomicMin) and the
-//       end-cell bit plane of the CTA's cell map
+//       end-cell bit of the CTA's cell map
+//   A3  beams that share an end cell have identical traces (same start, same end): only the owner io of each end
+//       cell -- the smallest index, which is also the one that decides every "free came first" question -- is put
+//       on the walk list (on the coarse levels this removes more than half of the beams)
 //   B1  free cells of all beams: one thread walks one beam with the reference's bresenham2D recurrence
 //       (OccGridMapBase.h:243-260) -- but in a 2-bit-per-cell map of the bounding box held in SHARED memory
 //       (free bit set with a shared-memory atomicOr, skipped when already set): the ~49 k scattered cell visits of a
@@ -567,6 +570,16 @@ __device__ __forceinline__ int hs_udiv_small(int x, int d, int& rem) {
   return q;
 }
 
+// 32-bit shared-window accesses for the walk loop (keeps the address arithmetic out of the generic space)
+__device__ __forceinline__ unsigned hs_lds_u32(unsigned addr) {
+  unsigned v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void hs_reds_or(unsigned addr, unsigned v) {
+  asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
 // End-cell hash table in shared memory: open addressing, linear probing, size = power of two >= 2 * max_points.
 __device__ __forceinline__ int hs_hash_slot(int cell, int log2_size) { return (int)(((unsigned)cell * 2654435761u) >> (32 - log2_size)); }
 
@@ -582,7 +595,7 @@ __device__ __forceinline__ int hs_hash_find(const int* __restrict__ keys, int ma
 }
 
 // dynamic shared memory: HS_MAP_BYTES (cell map) | hash keys[T] | hash vals[T] | max_points * sizeof(HsBeamRec),
-// T = hash_size (power of two >= 2 * max_points).
+// | max_points * sizeof(unsigned short) (walk list), T = hash_size (power of two >= 2 * max_points).
 __global__ void __launch_bounds__(HS_RAYCAST_THREADS) k_raycast(HsParams P, int n_slots, const int32_t* __restrict__ stream_ids,
                                                                 const float2* __restrict__ points, const int32_t* __restrict__ counts,
                                                                 const float2* __restrict__ origos, int log2_hash) {
@@ -592,7 +605,9 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS) k_raycast(HsParams P, int 
   int* hkeys = reinterpret_cast<int*>(hs_smem + HS_MAP_BYTES);             // end cell (grid offset) or EMPTY
   int* hvals = hkeys + hash_size;                                          // (io << 1) | free-came-first flag
   HsBeamRec* beams = reinterpret_cast<HsBeamRec*>(hvals + hash_size);
+  unsigned short* walk = reinterpret_cast<unsigned short*>(beams + P.max_points);   // owner beams, in index order per warp
   __shared__ int s_box[4];  // xmin, ymin, xmax, ymax over the start cell and all valid end cells
+  __shared__ int s_nwalk;
 
   int slot = blockIdx.x / P.n_levels;
   int level = blockIdx.x - slot * P.n_levels;
@@ -639,7 +654,7 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS) k_raycast(HsParams P, int 
     uint4* m4 = reinterpret_cast<uint4*>(hs_smem);
     for (int i = threadIdx.x; i < HS_MAP_BYTES / 16; i += blockDim.x) m4[i] = make_uint4(0u, 0u, 0u, 0u);
     for (int i = threadIdx.x; i < hash_size; i += blockDim.x) { hkeys[i] = HS_HASH_EMPTY; hvals[i] = INT_MAX; }
-    if (threadIdx.x == 0) { s_box[0] = INT_MAX; s_box[1] = INT_MAX; s_box[2] = INT_MIN; s_box[3] = INT_MIN; }
+    if (threadIdx.x == 0) { s_box[0] = INT_MAX; s_box[1] = INT_MAX; s_box[2] = INT_MIN; s_box[3] = INT_MIN; s_nwalk = 0; }
   }
   __syncthreads();
 
@@ -697,21 +712,41 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS) k_raycast(HsParams P, int 
   }
   __syncthreads();
 
-  // phase B1: free cells -- one thread per beam, the reference's bresenham2D recurrence (OccGridMapBase.h:243-260)
+  // phase A3: walk list = the owner beam of every end cell (ordered compaction: ballot + one atomicAdd per warp)
+  for (int i0 = 0; i0 < n; i0 += blockDim.x) {
+    const int i = i0 + threadIdx.x;
+    bool owner = false;
+    if (i < n && beams[i].da != 0) {
+      int h = hs_hash_find(hkeys, hash_mask, log2_hash, beams[i].kend);
+      owner = (hvals[h] >> 1) == i;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, owner);
+    int base = 0;
+    if (lane == 0 && m) base = atomicAdd(&s_nwalk, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (owner) walk[base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)i;
+  }
+  __syncthreads();
+
+  // phase B1: free cells -- one thread per walked beam, the reference's bresenham2D recurrence
+  // (OccGridMapBase.h:243-260)
   {
     const int row_step = use_map ? pitch : W;                       // address step of one cell in y
     const int k0 = use_map ? (by - y0) * pitch + (bx - x0) : by * W + bx;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int n_walk = s_nwalk;
+    const unsigned cmap_s = (unsigned)__cvta_generic_to_shared(cmap);
+    for (int wi = threadIdx.x; wi < n_walk; wi += blockDim.x) {
+      const int i = walk[wi];
       const HsBeamRec r = beams[i];
       const int da = r.da, db = r.db;
-      if (da == 0) continue;
       const int sa = (r.flags & 2) ? 1 : -1, sb = (r.flags & 4) ? 1 : -1;
       const int off_a = (r.flags & 1) ? sa : sa * row_step;
       const int off_b = (r.flags & 1) ? sb * row_step : sb;
       int k = k0, err = da >> 1;
       if (use_map) {
         for (int t = 0; t < da; ++t) {
-          const unsigned word = cmap[k >> 4];
+          const unsigned waddr = cmap_s + ((unsigned)(k >> 4) << 2);
+          const unsigned word = hs_lds_u32(waddr);
           const unsigned sh = (unsigned)k & 15u;
           if ((word >> (16u + sh)) & 1u) {
             // the free trace of beam i crosses a cell that is some beam's end point
@@ -723,7 +758,7 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS) k_raycast(HsParams P, int 
               if (i < (hv >> 1) && !(hv & 1)) atomicOr(&hvals[h], 1);
             }
           } else if (!((word >> sh) & 1u)) {
-            atomicOr(&cmap[k >> 4], 1u << sh);
+            hs_reds_or(waddr, 1u << sh);
           }
           k += off_a;
           err += db;
