@@ -43,7 +43,7 @@ FALLBACK_HBM_GBS = 6650.0  # B200_PROFILING.md fallback
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--streams", type=int, default=1024, help="streams per GPU (BASELINE configs[1])")
@@ -74,7 +74,7 @@ class ClockSampler(threading.Thread):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 if self.stop_flag.is_set():
@@ -230,7 +230,6 @@ def main():
     ev1.record(stream)
     barrier()
     ms_total = ev0.elapsed_time(ev1)
-    clocks = sampler.finish()
     ktimes = eng.profile_collect()
     eng.profile_enable(False)
     st1 = eng.stats()
@@ -262,6 +261,7 @@ def main():
         run_host(k)   # returns when this step's poses are valid in host memory
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    clocks = sampler.finish()      # sampled across both timed legs (device-resident and end-to-end)
     pose_checksum = float(h_pose.sum())
     e2e_scans, e2e_max_s = sharding.aggregate_throughput(S * K, e2e_s, device="cuda")
     e2e_value = e2e_scans / e2e_max_s
@@ -277,7 +277,16 @@ def main():
     per = {"k_match": (bytes_match, km["ms"] / max(km["launches"], 1)), "k_raycast": (bytes_ray, kr["ms"] / max(kr["launches"], 1))}
     dom = max(per, key=lambda n: per[n][1])
     ach = per[dom][0] / (per[dom][1] * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+    traffic, traffic_src = None, None
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tj = json.load(f)
+        if tj.get("streams_per_launch") == S and dom in tj.get("kernels", {}):
+            traffic, traffic_src = tj["kernels"][dom]["dram_bytes_per_launch"], tj.get("source")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                "traffic_source": traffic_src,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": per[dom][0], "avg_launch_ms": per[dom][1],
                 "kernels": {n: {"avg_launch_ms": per[n][1], "algorithmic_bytes_per_launch": per[n][0],
                                 "achieved_gbs": per[n][0] / (per[n][1] * 1e-3) / 1e9 if per[n][1] > 0 else None,

@@ -120,6 +120,11 @@ int hs_update_batch_ranges_device(hs_engine* e, int n, const int32_t* stream_ids
 /* Host helper with the same arithmetic (for callers that want DataContainer points). Returns the count. */
 int hs_scan_to_points_host(const float* ranges, int n_beams, float angle_min, float angle_increment,
                            float range_min, float range_max, float scale_to_map, float* points_out);
+/* The same for n_scans scans with `threads` host threads: points_out [n_scans][max_points][2] (zero padded),
+ * counts_out [n_scans]. */
+int hs_scan_to_points_host_batch(const float* ranges, int n_scans, int n_beams, float angle_min, float angle_increment,
+                                 float range_min, float range_max, float scale_to_map, int max_points,
+                                 float* points_out, int32_t* counts_out, int threads);
 
 /* getLastScanMatchPose / getLastScanMatchCovariance (HectorSlamProcessor.h:126-127) of streams
  * [first, first+n) into host memory. hs_get_last_map_update_poses exposes lastMapUpdatePose. */

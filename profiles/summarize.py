@@ -53,7 +53,7 @@ def kernels(tag, rep):
     idx = {h: i for i, h in enumerate(hdr)}
     seen = set()
     for r in raw[2:]:
-        name = r[idx["Kernel Name"]].split("(")[0].replace("void ", "").replace("<", "_").replace(">", "")
+        name = r[idx["Kernel Name"]].split("(")[0].replace("void ", "").replace("<", "_").replace(">", "").replace(", ", "_").replace(",", "_")
         if name in seen:
             continue
         seen.add(name)

@@ -103,6 +103,7 @@ def lib():
         "hs_update_batch_ranges": (_I, [_P, _I, _P, _P, _P, _P, _P, _P]),
         "hs_update_batch_ranges_device": (_I, [_P, _I, _P, _P, _P, _P]),
         "hs_scan_to_points_host": (_I, [_P, _I, _F, _F, _F, _F, _F, _P]),
+        "hs_scan_to_points_host_batch": (_I, [_P, _I, _I, _F, _F, _F, _F, _F, _I, _P, _P, _I]),
         "hs_get_poses": (_I, [_P, _I, _I, _P]), "hs_get_covariances": (_I, [_P, _I, _I, _P]),
         "hs_get_last_map_update_poses": (_I, [_P, _I, _I, _P]), "hs_device_pose_ptr": (_P, [_P]),
         "hs_hessian_derivs_batch": (_I, [_P, _I, _I, _P, _I, _P, _I, _P, _P]),
@@ -170,16 +171,11 @@ def scan_to_points_host(ranges, scene, scale_to_map, max_points=None):
     nb = ranges.shape[-1]
     mp = max_points or nb
     flat = ranges.reshape(-1, nb)
-    pts = np.zeros((flat.shape[0], mp, 2), np.float32)
-    cnt = np.zeros(flat.shape[0], np.int32)
-    tmp = np.zeros((nb, 2), np.float32)
-    fn = lib().hs_scan_to_points_host
-    for i in range(flat.shape[0]):
-        c = fn(flat[i].ctypes.data, nb, scene.angle_min, scene.angle_increment, scene.range_min, scene.range_max,
-               scale_to_map, tmp.ctypes.data)
-        c = min(c, mp)
-        pts[i, :c] = tmp[:c]
-        cnt[i] = c
+    pts = np.empty((flat.shape[0], mp, 2), np.float32)
+    cnt = np.empty(flat.shape[0], np.int32)
+    _check(lib().hs_scan_to_points_host_batch(flat.ctypes.data, flat.shape[0], nb, scene.angle_min, scene.angle_increment,
+                                              scene.range_min, scene.range_max, scale_to_map, mp, pts.ctypes.data,
+                                              cnt.ctypes.data, os.cpu_count() or 1), "hs_scan_to_points_host_batch")
     return pts.reshape(lead + (mp, 2)), cnt.reshape(lead)
 
 
