@@ -39,6 +39,7 @@ struct hs_engine {
   // bookkeeping
   uint64_t updates, launches, h2d_bytes, d2h_bytes;
   float free_factor, occ_factor;
+  int log2_seg_levels;       // k_raycast walk segment lengths (log2): level 0 | coarser levels << 8
   // optional per-kernel timing with CUDA events on the launching stream (hs_profile_*)
   int profiling;
   std::vector<cudaEvent_t>* prof_events;  // pairs: start, stop
@@ -93,7 +94,7 @@ static int raycast_log2_hash(int max_points) {
   return l;
 }
 static size_t raycast_smem_for(int max_points) {
-  return (size_t)HS_MAP_BYTES + 2 * sizeof(int) * ((size_t)1 << raycast_log2_hash(max_points)) + (size_t)max_points * sizeof(HsBeamRec) + (size_t)max_points * sizeof(unsigned short) + 16;
+  return (size_t)HS_MAP_BYTES + 2 * sizeof(int) * ((size_t)1 << raycast_log2_hash(max_points)) + (size_t)max_points * sizeof(HsWalkRec) + (size_t)max_points * sizeof(HsBeamRec) + 16;
 }
 static size_t raycast_smem(const hs_engine* e) { return raycast_smem_for(e->P.max_points); }
 static int warp_grid(int n_warps, int threads) { return (n_warps * 32 + threads - 1) / threads; }
@@ -201,6 +202,14 @@ int hs_create(const hs_config* cfg, hs_engine** out) {
     res *= 2.0f;
   }
   P.cells_per_stream = off;
+  {
+    int s0 = 5, s1 = 4;   // 32-step segments on the fine grid, 16-step segments on the coarse ones
+    const char* env = getenv("HSGPU_RAYCAST_SEG_LOG2");   // tuning hook: "<level0>,<coarse>"
+    if (env) sscanf(env, "%d,%d", &s0, &s1);
+    s0 = s0 < 2 ? 2 : (s0 > 12 ? 12 : s0);
+    s1 = s1 < 2 ? 2 : (s1 > 12 ? 12 : s1);
+    e->log2_seg_levels = s0 | (s1 << 8);
+  }
   e->free_factor = 0.4f;
   e->occ_factor = 0.6f;
   P.log_odds_free = prob_to_log_odds(0.4f);
@@ -227,6 +236,7 @@ int hs_create(const hs_config* cfg, hs_engine** out) {
   HS_ALLOC(P.coarse_cnt, ns * sizeof(int));
   HS_ALLOC(P.coarse_origo, ns * 2 * sizeof(float));
   HS_ALLOC(P.slot_pose, ns * 3 * sizeof(float));
+  HS_ALLOC(P.slot_sc, ns * 2 * sizeof(float));
   HS_ALLOC(P.slot_integrate, ns * sizeof(int));
   HS_ALLOC(P.slot_mark_base, ns * sizeof(int));
   HS_ALLOC(P.counters, 4 * sizeof(unsigned long long));
@@ -289,7 +299,7 @@ int hs_destroy(hs_engine* e) {
   if (e->own_stream) cudaStreamSynchronize(e->own_stream);
   HsParams& P = e->P;
   void* ptrs[] = {P.val, P.idx, P.last_pose, P.last_update_pose, P.cov, P.cur_update_index, P.last_update_index,
-                  P.coarse_pts, P.coarse_cnt, P.coarse_origo, P.slot_pose, P.slot_integrate, P.slot_mark_base, P.counters,
+                  P.coarse_pts, P.coarse_cnt, P.coarse_origo, P.slot_pose, P.slot_sc, P.slot_integrate, P.slot_mark_base, P.counters,
                   e->d_points, e->d_counts, e->d_origos, e->d_hints, e->d_flags, e->d_ids, e->d_ranges, e->d_out,
                   e->d_beam_cs, e->d_scratch};
   for (void* p : ptrs)
@@ -412,7 +422,7 @@ static int run_update_device(hs_engine* e, int n, const int32_t* ids, const floa
     {
       ProfScope ps(e, HS_K_RAYCAST);
       k_raycast<<<n * e->P.n_levels, HS_RAYCAST_THREADS, raycast_smem(e), e->stream>>>(
-          e->P, n, ids, (const float2*)points, counts, (const float2*)origos, raycast_log2_hash(e->P.max_points));
+          e->P, n, ids, (const float2*)points, counts, (const float2*)origos, raycast_log2_hash(e->P.max_points), e->log2_seg_levels);
     }
     HS_LAUNCHED(e);
   }
@@ -646,7 +656,7 @@ int hs_raycast_batch(hs_engine* e, int n, const int32_t* stream_ids, const float
   k_force_integrate<<<warp_grid(n, threads), threads, 0, e->stream>>>(e->P, n, d_ids, (const float2*)e->d_points, e->d_counts, d_or, e->d_hints);
   HS_LAUNCHED(e);
   k_raycast<<<n * e->P.n_levels, HS_RAYCAST_THREADS, raycast_smem(e), e->stream>>>(
-      e->P, n, d_ids, (const float2*)e->d_points, e->d_counts, d_or, raycast_log2_hash(e->P.max_points));
+      e->P, n, d_ids, (const float2*)e->d_points, e->d_counts, d_or, raycast_log2_hash(e->P.max_points), e->log2_seg_levels);
   HS_LAUNCHED(e);
   HS_CK(cudaStreamSynchronize(e->stream));
   return HS_OK;

@@ -56,6 +56,7 @@ struct HsParams {
   float* coarse_origo;       // [n_streams][2]
   // per-slot (one slot = one stream update in the current batch)
   float* slot_pose;          // [n_streams][3] pose the ray-caster integrates with
+  float* slot_sc;            // [n_streams][2] sinf / cosf of that pose's angle (computed once, by the gate)
   int* slot_integrate;       // [n_streams]    gate result
   int* slot_mark_base;       // [n_streams]    currUpdateIndex at the start of this scan's integration
   unsigned long long* counters;  // [0] unused [1] integrations [2] angle clamps [3] ray-cast cell visits
@@ -428,6 +429,7 @@ __global__ void __launch_bounds__(HS_MATCH_THREADS) k_match(HsParams P, int n_sl
         P.cur_update_index[s] = cur + 3;        // OccGridMapBase.h:167
         P.last_update_index[s] += 1;            // setUpdated() (OccGridMapBase.h:164)
         P.slot_pose[3 * slot] = wx; P.slot_pose[3 * slot + 1] = wy; P.slot_pose[3 * slot + 2] = wth;
+        P.slot_sc[2 * slot] = hs_sinf(wth); P.slot_sc[2 * slot + 1] = hs_cosf(wth);   // Rotation2Df(pose[2]) of updateByScan (OccGridMapBase.h:130)
         atomicAdd(&P.counters[1], 1ULL);
       }
     }
@@ -459,6 +461,7 @@ __global__ void __launch_bounds__(128) k_force_integrate(HsParams P, int n_slots
     P.cur_update_index[s] = cur + 3;
     P.last_update_index[s] += 1;
     P.slot_pose[3 * slot] = poses[3 * slot]; P.slot_pose[3 * slot + 1] = poses[3 * slot + 1]; P.slot_pose[3 * slot + 2] = poses[3 * slot + 2];
+    P.slot_sc[2 * slot] = hs_sinf(poses[3 * slot + 2]); P.slot_sc[2 * slot + 1] = hs_cosf(poses[3 * slot + 2]);
     P.slot_integrate[slot] = 1;
     atomicAdd(&P.counters[1], 1ULL);
   }
@@ -560,6 +563,14 @@ struct HsBeamRec {
   unsigned int flags;          // bit0: dominant axis is x, bit1: step along a is +, bit2: step along b is +
 };
 
+// Walk record: one per end-cell owner beam, everything the free-cell walk needs in one 16-byte shared load.
+struct __align__(16) HsWalkRec {
+  unsigned dadb;               // abs_da | abs_db << 16
+  unsigned offs;               // cell-address step along the dominant axis (low 16 bits, signed) | along the minor axis << 16
+  int beam;                    // beam index (the reference's loop position; decides "free came first")
+  int seg_start;               // index of this beam's first walk segment (ascending over the walk list)
+};
+
 // exact x / d for 0 <= x < 2^22, 0 < d < 2^22: approximate float quotient (MUFU.RCP, <= 2 ulp) + one-step correction
 __device__ __forceinline__ int hs_udiv_small(int x, int d, int& rem) {
   int q = (int)__fdividef((float)x, (float)d);
@@ -579,6 +590,12 @@ __device__ __forceinline__ unsigned hs_lds_u32(unsigned addr) {
 __device__ __forceinline__ void hs_reds_or(unsigned addr, unsigned v) {
   asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
+// shared-window address of a generic pointer, computed ONCE (volatile: the compiler may not re-derive it per use)
+__device__ __forceinline__ unsigned hs_shared_addr(const void* p) {
+  unsigned a;
+  asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(a) : "l"(p));
+  return a;
+}
 
 // End-cell hash table in shared memory: open addressing, linear probing, size = power of two >= 2 * max_points.
 __device__ __forceinline__ int hs_hash_slot(int cell, int log2_size) { return (int)(((unsigned)cell * 2654435761u) >> (32 - log2_size)); }
@@ -594,20 +611,33 @@ __device__ __forceinline__ int hs_hash_find(const int* __restrict__ keys, int ma
   }
 }
 
-// dynamic shared memory: HS_MAP_BYTES (cell map) | hash keys[T] | hash vals[T] | max_points * sizeof(HsBeamRec),
-// | max_points * sizeof(unsigned short) (walk list), T = hash_size (power of two >= 2 * max_points).
+// a free trace reaches a cell that is some beam's end point: only "did a free trace of an EARLIER beam cross it" matters
+__device__ __forceinline__ void hs_free_hits_end_cell(const int* __restrict__ hkeys, int* __restrict__ hvals, int hash_mask, int log2_hash,
+                                                      int cell, int beam) {
+  int h = hs_hash_find(hkeys, hash_mask, log2_hash, cell);
+  if (h >= 0) {
+    int hv = hvals[h];
+    if (beam < (hv >> 1) && !(hv & 1)) atomicOr(&hvals[h], 1);
+  }
+}
+
+// dynamic shared memory: HS_MAP_BYTES (cell map) | hash keys[T] | hash vals[T] | max_points * sizeof(HsWalkRec)
+// | max_points * sizeof(HsBeamRec), T = hash_size (power of two >= 2 * max_points).
+// log2_seg_levels: the free-cell walk is cut into segments of 2^k steps that are dealt out evenly to the threads
+// (k = low byte on level 0, next byte on the coarser levels).
 __global__ void __launch_bounds__(HS_RAYCAST_THREADS) k_raycast(HsParams P, int n_slots, const int32_t* __restrict__ stream_ids,
                                                                 const float2* __restrict__ points, const int32_t* __restrict__ counts,
-                                                                const float2* __restrict__ origos, int log2_hash) {
+                                                                const float2* __restrict__ origos, int log2_hash, int log2_seg_levels) {
   extern __shared__ __align__(16) unsigned char hs_smem[];
   const int hash_size = 1 << log2_hash, hash_mask = hash_size - 1;
   unsigned* cmap = reinterpret_cast<unsigned*>(hs_smem);                   // 16 cells per word: free bits | end bits << 16
   int* hkeys = reinterpret_cast<int*>(hs_smem + HS_MAP_BYTES);             // end cell (grid offset) or EMPTY
   int* hvals = hkeys + hash_size;                                          // (io << 1) | free-came-first flag
-  HsBeamRec* beams = reinterpret_cast<HsBeamRec*>(hvals + hash_size);
-  unsigned short* walk = reinterpret_cast<unsigned short*>(beams + P.max_points);   // owner beams, in index order per warp
+  HsWalkRec* walk = reinterpret_cast<HsWalkRec*>(hvals + hash_size);       // owner beams
+  HsBeamRec* beams = reinterpret_cast<HsBeamRec*>(walk + P.max_points);
   __shared__ int s_box[4];  // xmin, ymin, xmax, ymax over the start cell and all valid end cells
-  __shared__ int s_nwalk;
+  __shared__ unsigned long long s_alloc;   // walk-list allocator: owners << 32 | segments
+  __shared__ unsigned s_visits;
 
   int slot = blockIdx.x / P.n_levels;
   int level = blockIdx.x - slot * P.n_levels;
@@ -618,6 +648,7 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS) k_raycast(HsParams P, int 
   float* val = P.val + (size_t)s * P.cells_per_stream + L.cell_offset;
   int* idx = P.idx + (size_t)s * P.cells_per_stream + L.cell_offset;
   const int W = L.sx;
+  const int T = blockDim.x;
 
   // level 0 integrates the scan itself, level i > 0 the container last refreshed by matchData
   // (MapRepMultiMap.h:134-147) -- possibly stale or empty when map_without_matching was used.
@@ -642,48 +673,46 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS) k_raycast(HsParams P, int 
 
   float mpx, mpy;
   hs_world_to_map(L, P.slot_pose[3 * slot], P.slot_pose[3 * slot + 1], mpx, mpy);
-  float th = P.slot_pose[3 * slot + 2];
-  float sn = hs_sinf(th), cs = hs_cosf(th);
+  const float sn = P.slot_sc[2 * slot], cs = P.slot_sc[2 * slot + 1];   // sinf / cosf of the pose angle, from the gate
   const int bx = (int)(((cs * ox + (-sn) * oy) + mpx) + 0.5f);  // Vector2i(float, float): truncation (OccGridMapBase.h:137)
   const int by = (int)(((sn * ox + cs * oy) + mpy) + 0.5f);
   const float pf = L.pt_factor;
   const int lane = threadIdx.x & 31;
 
-  // clear the cell map and the hash table (independent of everything else), reset the box
-  {
-    uint4* m4 = reinterpret_cast<uint4*>(hs_smem);
-    for (int i = threadIdx.x; i < HS_MAP_BYTES / 16; i += blockDim.x) m4[i] = make_uint4(0u, 0u, 0u, 0u);
-    for (int i = threadIdx.x; i < hash_size; i += blockDim.x) { hkeys[i] = HS_HASH_EMPTY; hvals[i] = INT_MAX; }
-    if (threadIdx.x == 0) { s_box[0] = INT_MAX; s_box[1] = INT_MAX; s_box[2] = INT_MIN; s_box[3] = INT_MIN; s_nwalk = 0; }
-  }
+  // clear the hash table, reset the box and the allocators
+  for (int i = threadIdx.x; i < hash_size; i += T) { hkeys[i] = HS_HASH_EMPTY; hvals[i] = INT_MAX; }
+  if (threadIdx.x == 0) { s_box[0] = INT_MAX; s_box[1] = INT_MAX; s_box[2] = INT_MIN; s_box[3] = INT_MIN; s_alloc = 0ULL; s_visits = 0u; }
   __syncthreads();
 
   // phase A1: one thread per beam -- beam record and bounding box
-  unsigned visits = 0;
-  int xmin = INT_MAX, ymin = INT_MAX, xmax = INT_MIN, ymax = INT_MIN;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    float2 p = pts[i];
-    HsBeam b = hs_make_beam(L, bx, by, mpx, mpy, sn, cs, p.x * pf, p.y * pf);
-    HsBeamRec r;
-    r.kend = b.kend; r.da = 0; r.db = (unsigned short)b.abs_db;
-    r.flags = (unsigned)((b.a_is_x ? 1 : 0) | (b.sa > 0 ? 2 : 0) | (b.sb > 0 ? 4 : 0));
-    if (b.valid) {
-      visits += b.abs_da + 1u;
-      r.da = (unsigned short)b.abs_da;
-      xmin = min(xmin, b.ex); xmax = max(xmax, b.ex); ymin = min(ymin, b.ey); ymax = max(ymax, b.ey);
+  {
+    unsigned visits = 0;
+    int xmin = INT_MAX, ymin = INT_MAX, xmax = INT_MIN, ymax = INT_MIN;
+    for (int i = threadIdx.x; i < n; i += T) {
+      float2 p = pts[i];
+      HsBeam b = hs_make_beam(L, bx, by, mpx, mpy, sn, cs, p.x * pf, p.y * pf);
+      HsBeamRec r;
+      r.kend = b.kend; r.da = 0; r.db = (unsigned short)b.abs_db;
+      r.flags = (unsigned)((b.a_is_x ? 1 : 0) | (b.sa > 0 ? 2 : 0) | (b.sb > 0 ? 4 : 0));
+      if (b.valid) {
+        visits += b.abs_da + 1u;
+        r.da = (unsigned short)b.abs_da;
+        xmin = min(xmin, b.ex); xmax = max(xmax, b.ex); ymin = min(ymin, b.ey); ymax = max(ymax, b.ey);
+      }
+      beams[i] = r;
     }
-    beams[i] = r;
-  }
-  visits = __reduce_add_sync(0xffffffffu, visits);
-  xmin = __reduce_min_sync(0xffffffffu, xmin); ymin = __reduce_min_sync(0xffffffffu, ymin);
-  xmax = __reduce_max_sync(0xffffffffu, xmax); ymax = __reduce_max_sync(0xffffffffu, ymax);
-  if (lane == 0 && visits) {
-    atomicAdd(&P.counters[3], (unsigned long long)visits);
-    atomicMin(&s_box[0], min(xmin, bx)); atomicMin(&s_box[1], min(ymin, by));
-    atomicMax(&s_box[2], max(xmax, bx)); atomicMax(&s_box[3], max(ymax, by));
+    visits = __reduce_add_sync(0xffffffffu, visits);
+    xmin = __reduce_min_sync(0xffffffffu, xmin); ymin = __reduce_min_sync(0xffffffffu, ymin);
+    xmax = __reduce_max_sync(0xffffffffu, xmax); ymax = __reduce_max_sync(0xffffffffu, ymax);
+    if (lane == 0 && visits) {
+      atomicAdd(&s_visits, visits);
+      atomicMin(&s_box[0], min(xmin, bx)); atomicMin(&s_box[1], min(ymin, by));
+      atomicMax(&s_box[2], max(xmax, bx)); atomicMax(&s_box[3], max(ymax, by));
+    }
   }
   __syncthreads();
   if (s_box[2] < s_box[0]) return;  // no valid beam (uniform for the CTA)
+  if (threadIdx.x == 0) atomicAdd(&P.counters[3], (unsigned long long)s_visits);
 
   // geometry of the cell map: rows of `pitch` cells starting at a 32-aligned x0; the row pitch in words is odd so
   // that a vertical run of cells spreads over the shared-memory banks
@@ -692,9 +721,15 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS) k_raycast(HsParams P, int 
   const int pw = (((x1 - x0) >> 4) + 1) | 1;   // 16-cell words per map row
   const int pitch = pw << 4;                   // cells per map row
   const bool use_map = (long long)pitch * bh <= HS_MAP_CELLS;
+  if (use_map) {   // clear the part of the cell map this scan uses
+    uint4* m4 = reinterpret_cast<uint4*>(hs_smem);
+    const int n4 = (pw * bh + 3) >> 2;
+    for (int i = threadIdx.x; i < n4; i += T) m4[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+  }
 
   // phase A2: end point ownership -- io = smallest beam index per end cell
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+  for (int i = threadIdx.x; i < n; i += T) {
     const HsBeamRec r = beams[i];
     if (r.da == 0) continue;
     int h = hs_hash_slot(r.kend, log2_hash);
@@ -712,109 +747,171 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS) k_raycast(HsParams P, int 
   }
   __syncthreads();
 
-  // phase A3: walk list = the owner beam of every end cell (ordered compaction: ballot + one atomicAdd per warp)
-  for (int i0 = 0; i0 < n; i0 += blockDim.x) {
+  // phase A3: walk list = the owner beam of every end cell. Beams that share an end cell have identical traces (same
+  // start, same end), and the owner -- the smallest index -- is the one that decides every "free came first" question.
+  // Each owner's trace is cut into segments of `seg` steps; one 64-bit shared atomicAdd per warp hands out list
+  // positions and segment indices together, so seg_start ascends along the list.
+  const int log2_seg = level == 0 ? (log2_seg_levels & 0xFF) : (log2_seg_levels >> 8);   // per level: fine grid / coarse grids
+  const int seg = 1 << log2_seg;
+  const int row_step = use_map ? pitch : W;                       // address step of one cell in y
+  for (int i0 = 0; i0 < n; i0 += T) {
     const int i = i0 + threadIdx.x;
     bool owner = false;
-    if (i < n && beams[i].da != 0) {
-      int h = hs_hash_find(hkeys, hash_mask, log2_hash, beams[i].kend);
-      owner = (hvals[h] >> 1) == i;
+    HsBeamRec r;
+    r.kend = 0; r.da = 0; r.db = 0; r.flags = 0;
+    if (i < n) {
+      r = beams[i];
+      if (r.da != 0) {
+        int h = hs_hash_find(hkeys, hash_mask, log2_hash, r.kend);
+        owner = (hvals[h] >> 1) == i;
+      }
+    }
+    const int nseg = owner ? ((int)r.da + seg - 1) >> log2_seg : 0;
+    int incl = nseg;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
     }
     const unsigned m = __ballot_sync(0xffffffffu, owner);
-    int base = 0;
-    if (lane == 0 && m) base = atomicAdd(&s_nwalk, __popc(m));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (owner) walk[base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)i;
-  }
-  __syncthreads();
-
-  // phase B1: free cells -- one thread per walked beam, the reference's bresenham2D recurrence
-  // (OccGridMapBase.h:243-260)
-  {
-    const int row_step = use_map ? pitch : W;                       // address step of one cell in y
-    const int k0 = use_map ? (by - y0) * pitch + (bx - x0) : by * W + bx;
-    const int n_walk = s_nwalk;
-    const unsigned cmap_s = (unsigned)__cvta_generic_to_shared(cmap);
-    for (int wi = threadIdx.x; wi < n_walk; wi += blockDim.x) {
-      const int i = walk[wi];
-      const HsBeamRec r = beams[i];
-      const int da = r.da, db = r.db;
+    unsigned long long base = 0ULL;
+    if (lane == 31 && m) base = atomicAdd(&s_alloc, ((unsigned long long)__popc(m) << 32) | (unsigned long long)(unsigned)incl);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    if (owner) {
       const int sa = (r.flags & 2) ? 1 : -1, sb = (r.flags & 4) ? 1 : -1;
       const int off_a = (r.flags & 1) ? sa : sa * row_step;
       const int off_b = (r.flags & 1) ? sb * row_step : sb;
-      int k = k0, err = da >> 1;
-      if (use_map) {
-        for (int t = 0; t < da; ++t) {
-          const unsigned waddr = cmap_s + ((unsigned)(k >> 4) << 2);
+      HsWalkRec w;
+      w.dadb = (unsigned)r.da | ((unsigned)r.db << 16);
+      w.offs = ((unsigned)off_a & 0xFFFFu) | ((unsigned)off_b << 16);
+      w.beam = i;
+      w.seg_start = (int)(unsigned)(base & 0xFFFFFFFFULL) + incl - nseg;
+      walk[(int)(base >> 32) + __popc(m & ((1u << lane) - 1u))] = w;
+    }
+  }
+  __syncthreads();
+  const int n_walk = (int)(s_alloc >> 32), n_items = (int)(unsigned)(s_alloc & 0xFFFFFFFFULL);
+
+  // phase B1: free cells with the reference's bresenham2D recurrence (OccGridMapBase.h:243-260). Every thread takes
+  // the same number of consecutive walk segments (so the longest beam no longer sets the CTA's pace); a thread that
+  // starts inside a beam enters the recurrence through its closed form after t steps:
+  //   cell(t) = k0 + t*off_a + floor((abs_da/2 + t*abs_db) / abs_da) * off_b,  err(t) = (abs_da/2 + t*abs_db) mod abs_da.
+  // Marks go to the 2-bit-per-cell map of the bounding box in SHARED memory: the ~49 k scattered cell visits of a scan
+  // never reach L2/HBM.
+  if (use_map) {
+    const int k0 = (by - y0) * pitch + (bx - x0);
+    const unsigned cmap_s = hs_shared_addr(cmap);
+    const int per = (n_items + T - 1) / T;
+    int j = threadIdx.x * per;
+    const int j1 = min(j + per, n_items);
+    if (j < j1) {
+      int lo = 0, hi = n_walk - 1;       // largest p with walk[p].seg_start <= j
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (walk[mid].seg_start <= j) lo = mid; else hi = mid - 1;
+      }
+      int p = lo;
+      HsWalkRec w = walk[p];
+      int da = (int)(w.dadb & 0xFFFFu), db = (int)(w.dadb >> 16);
+      int off_a = (int)(short)(w.offs & 0xFFFFu), off_b = ((int)w.offs) >> 16;
+      int beam = w.beam;
+      const int t0 = (j - w.seg_start) << log2_seg;
+      const int e0 = (da >> 1) + t0 * db;
+      const int q0 = e0 / da;
+      int k = k0 + t0 * off_a + q0 * off_b, err = e0 - q0 * da, rem = da - t0;
+      for (; j < j1; ++j) {
+        const int steps = min(seg, rem);
+        for (int t = 0; t < steps; ++t) {
+          const unsigned waddr = cmap_s + (((unsigned)k >> 4) << 2);
           const unsigned word = hs_lds_u32(waddr);
-          const unsigned sh = (unsigned)k & 15u;
-          if ((word >> (16u + sh)) & 1u) {
-            // the free trace of beam i crosses a cell that is some beam's end point
-            int xx;
-            int yy = hs_udiv_small(k, pitch, xx);
-            int h = hs_hash_find(hkeys, hash_mask, log2_hash, (yy + y0) * W + (xx + x0));
-            if (h >= 0) {
-              int hv = hvals[h];
-              if (i < (hv >> 1) && !(hv & 1)) atomicOr(&hvals[h], 1);
-            }
-          } else if (!((word >> sh) & 1u)) {
-            hs_reds_or(waddr, 1u << sh);
+          const unsigned mbit = 0x10001u << ((unsigned)k & 15u);
+          const unsigned hit = word & mbit;
+          if (hit == 0u) {
+            hs_reds_or(waddr, mbit & 0xFFFFu);
+          } else if (hit & 0xFFFF0000u) {   // the free trace crosses a cell that is some beam's end point
+            const int yy = k / pitch, xx = k - yy * pitch;
+            hs_free_hits_end_cell(hkeys, hvals, hash_mask, log2_hash, (yy + y0) * W + (xx + x0), beam);
           }
           k += off_a;
           err += db;
           if (err >= da) { k += off_b; err -= da; }
         }
-      } else {
-        for (int t = 0; t < da; ++t) {
-          int h = hs_hash_find(hkeys, hash_mask, log2_hash, k);
-          if (h >= 0) {                 // end cell: only the "free came first" flag matters
-            int hv = hvals[h];
-            if (i < (hv >> 1) && !(hv & 1)) atomicOr(&hvals[h], 1);
-          } else if (idx[k] < mark_free) {  // may be served by L1: a stale "not yet marked" only repeats an idempotent store
-            idx[k] = mark_free;
-          }
-          k += off_a;
-          err += db;
-          if (err >= da) { k += off_b; err -= da; }
+        rem -= steps;
+        if (rem == 0 && j + 1 < j1) {
+          w = walk[++p];
+          da = (int)(w.dadb & 0xFFFFu); db = (int)(w.dadb >> 16);
+          off_a = (int)(short)(w.offs & 0xFFFFu); off_b = ((int)w.offs) >> 16;
+          beam = w.beam;
+          k = k0; err = da >> 1; rem = da;
         }
+      }
+    }
+  } else {
+    // the bounding box does not fit the cell map: mark in the global marker plane (idx = markFree by plain,
+    // idempotent stores); one thread per owner beam
+    const int k0 = by * W + bx;
+    for (int wi = threadIdx.x; wi < n_walk; wi += T) {
+      const HsWalkRec w = walk[wi];
+      const int da = (int)(w.dadb & 0xFFFFu), db = (int)(w.dadb >> 16);
+      const int off_a = (int)(short)(w.offs & 0xFFFFu), off_b = ((int)w.offs) >> 16;
+      int k = k0, err = da >> 1;
+      for (int t = 0; t < da; ++t) {
+        int h = hs_hash_find(hkeys, hash_mask, log2_hash, k);
+        if (h >= 0) {                 // end cell: only the "free came first" flag matters
+          int hv = hvals[h];
+          if (w.beam < (hv >> 1) && !(hv & 1)) atomicOr(&hvals[h], 1);
+        } else if (idx[k] < mark_free) {  // may be served by L1: a stale "not yet marked" only repeats an idempotent store
+          idx[k] = mark_free;
+        }
+        k += off_a;
+        err += db;
+        if (err >= da) { k += off_b; err -= da; }
       }
     }
   }
   __syncthreads();
 
-  // phase B2: updateSetFree exactly once per marked cell -- coalesced sweep of the bounding box, one warp per row.
+  // phase B2: updateSetFree exactly once per marked cell -- coalesced sweep of the bounding box.
   const bool vec_ok = use_map && ((W & 3) == 0) && ((reinterpret_cast<uintptr_t>(val) & 15) == 0);
   if (vec_ok) {
-    // fast path: a lane owns 4 consecutive cells (one float4), a warp covers 128 cells per step. Unmarked
-    // components are written back unchanged, hence the barrier before phase C touches the end cells.
-    const int warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-    const int chunks = ((x1 - x0) >> 7) + 1;
-    for (int ry = warp; ry < bh; ry += n_warps) {
-      const int row = (y0 + ry) * W + x0 + (lane << 2);
-      const unsigned* mrow = cmap + ry * pw + (lane >> 2);
-      const unsigned sh = (unsigned)(lane & 3) << 2;
-      for (int c0 = 0; c0 < chunks; c0 += 2) {
-        unsigned bits[2];
-        float4 v[2];
+    // fast path: the box is a list of aligned 4-cell quads (one float4 of log-odds, 4 map bits), dealt out to the threads
+    // in row-major order, four quads in flight per thread. Unmarked components are written back unchanged, hence the
+    // barrier before phase C touches the end cells.
+    const int qpr = ((x1 - x0) >> 2) + 1;     // quads per box row (x0 is 32-aligned, W a multiple of 4)
+    const int nq = qpr * bh;
+    const int4 mf4 = make_int4(mark_free, mark_free, mark_free, mark_free);
+    for (int q0 = threadIdx.x; q0 < nq; q0 += 4 * T) {
+      unsigned bits[4];
+      int g[4];
+      float4 v[4];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int c = c0 + u;
-          bits[u] = 0u;
-          if (c < chunks && x0 + (c << 7) + (lane << 2) <= x1) {
-            bits[u] = (mrow[c << 3] >> sh) & 0xFu;
-            if (bits[u]) v[u] = *reinterpret_cast<const float4*>(val + row + (c << 7));
-          }
+      for (int u = 0; u < 4; ++u) {
+        const int q = q0 + u * T;
+        bits[u] = 0u;
+        if (q < nq) {
+          int c;
+          const int ry = hs_udiv_small(q, qpr, c);
+          bits[u] = (cmap[ry * pw + (c >> 2)] >> ((unsigned)(c & 3) << 2)) & 0xFu;
+          g[u] = (y0 + ry) * W + x0 + (c << 2);
+          if (bits[u]) v[u] = *reinterpret_cast<const float4*>(val + g[u]);
         }
+      }
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          if (bits[u]) {
-            const int g = row + ((c0 + u) << 7);
-            float4 w = v[u];
-            if (bits[u] & 1u) { w.x = w.x + f; idx[g] = mark_free; }
-            if (bits[u] & 2u) { w.y = w.y + f; idx[g + 1] = mark_free; }
-            if (bits[u] & 4u) { w.z = w.z + f; idx[g + 2] = mark_free; }
-            if (bits[u] & 8u) { w.w = w.w + f; idx[g + 3] = mark_free; }
-            *reinterpret_cast<float4*>(val + g) = w;
+      for (int u = 0; u < 4; ++u) {
+        if (bits[u]) {
+          float4 w = v[u];
+          if (bits[u] & 1u) w.x = w.x + f;
+          if (bits[u] & 2u) w.y = w.y + f;
+          if (bits[u] & 4u) w.z = w.z + f;
+          if (bits[u] & 8u) w.w = w.w + f;
+          *reinterpret_cast<float4*>(val + g[u]) = w;
+          if (bits[u] == 0xFu) {
+            *reinterpret_cast<int4*>(idx + g[u]) = mf4;
+          } else {
+            if (bits[u] & 1u) idx[g[u]] = mark_free;
+            if (bits[u] & 2u) idx[g[u] + 1] = mark_free;
+            if (bits[u] & 4u) idx[g[u] + 2] = mark_free;
+            if (bits[u] & 8u) idx[g[u] + 3] = mark_free;
           }
         }
       }
@@ -852,20 +949,18 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS) k_raycast(HsParams P, int 
     }
   }
 
-  // phase C: end points -- the beam that owns io applies undo-free / occupied and stores markOcc
-  // (end cells are disjoint from the cells B2 writes: their free bit / free marker is never set)
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const HsBeamRec r = beams[i];
-    if (r.da == 0) continue;
-    int h = hs_hash_find(hkeys, hash_mask, log2_hash, r.kend);
-    int hv = hvals[h];
-    if ((hv >> 1) == i) {
-      float v = val[r.kend];
-      if (hv & 1) v = (v + f) - f;       // updateSetFree by an earlier beam, then updateUnsetFree
-      if (v < 50.0f) v = v + o;          // updateSetOccupied
-      val[r.kend] = v;
-      idx[r.kend] = mark_occ;
-    }
+  // phase C: end points -- the owner beam applies undo-free / occupied and stores markOcc
+  // (end cells are disjoint from the cells B2 marks: their free bit / free marker is never set)
+  for (int wi = threadIdx.x; wi < n_walk; wi += T) {
+    const int i = walk[wi].beam;
+    const int kend = beams[i].kend;
+    const int h = hs_hash_find(hkeys, hash_mask, log2_hash, kend);
+    const int hv = hvals[h];
+    float v = val[kend];
+    if (hv & 1) v = (v + f) - f;       // updateSetFree by an earlier beam, then updateUnsetFree
+    if (v < 50.0f) v = v + o;          // updateSetOccupied
+    val[kend] = v;
+    idx[kend] = mark_occ;
   }
 }
 
