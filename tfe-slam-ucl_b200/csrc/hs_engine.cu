@@ -175,6 +175,7 @@ int hs_create(const hs_config* cfg, hs_engine** out) {
   P.n_levels = cfg->levels;
   P.n_streams = cfg->n_streams;
   P.max_points = cfg->max_points;
+  { const char* d = getenv("HSGPU_DEBUG_SKIP"); P.dbg_skip = d ? atoi(d) : 0; }   // timing experiments only: results are wrong when set
   P.strict = 1;  // reference-order sums by default: bitwise the CPU reference's poses
 
   // MapRepMultiMap ctor (HSL/slam_main/MapRepMultiMap.h:48-72): same world offset for every level,
@@ -277,6 +278,9 @@ int hs_create(const hs_config* cfg, hs_engine** out) {
       }
     }
   }
+  if (getenv("HSGPU_DEBUG_TIMES")) {   // timing experiments only
+    if (cudaMalloc((void**)&P.dbg_times, ns * HS_MAX_LEVELS * 8 * sizeof(unsigned long long)) != cudaSuccess) P.dbg_times = nullptr;
+  }
   cudaMemsetAsync(P.counters, 0, 4 * sizeof(unsigned long long), e->stream);
   cudaMemsetAsync(P.slot_integrate, 0, ns * sizeof(int), e->stream);
   cudaMemsetAsync(P.coarse_pts, 0, ns * mp * 2 * sizeof(float), e->stream);
@@ -297,6 +301,17 @@ int hs_destroy(hs_engine* e) {
   if (!e) return HS_OK;
   cudaSetDevice(e->device);
   if (e->own_stream) cudaStreamSynchronize(e->own_stream);
+  if (e->P.dbg_times) {   // timing experiments only: dump the stamps of the last ray-cast launch
+    const char* path = getenv("HSGPU_DEBUG_TIMES");
+    size_t n = (size_t)e->P.n_streams * HS_MAX_LEVELS * 8;
+    std::vector<unsigned long long> h(n);
+    cudaDeviceSynchronize();
+    if (path && cudaMemcpy(h.data(), e->P.dbg_times, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess) {
+      FILE* f = fopen(path, "wb");
+      if (f) { fwrite(h.data(), sizeof(unsigned long long), n, f); fclose(f); }
+    }
+    cudaFree(e->P.dbg_times);
+  }
   HsParams& P = e->P;
   void* ptrs[] = {P.val, P.idx, P.last_pose, P.last_update_pose, P.cov, P.cur_update_index, P.last_update_index,
                   P.coarse_pts, P.coarse_cnt, P.coarse_origo, P.slot_pose, P.slot_sc, P.slot_integrate, P.slot_mark_base, P.counters,

@@ -37,6 +37,8 @@ struct HsParams {
   int n_levels;
   int n_streams;
   int max_points;
+  int dbg_skip;                     // timing experiments only (HSGPU_DEBUG_SKIP): bit0 skip walk, bit1 skip sweep, bit2 skip end points
+  unsigned long long* dbg_times;    // timing experiments only (HSGPU_DEBUG_TIMES): 8 globaltimer stamps per ray-cast CTA
   int strict;                       // 1: accumulate H/dTr in the reference's sequential point order
   unsigned long long cells_per_stream;
   HsLevel lv[HS_MAX_LEVELS];
@@ -597,6 +599,14 @@ __device__ __forceinline__ unsigned hs_shared_addr(const void* p) {
   return a;
 }
 
+__device__ __forceinline__ void hs_stamp(const HsParams& P, int k) {
+  if (P.dbg_times && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    P.dbg_times[(size_t)blockIdx.x * 8 + k] = t;
+  }
+}
+
 // End-cell hash table in shared memory: open addressing, linear probing, size = power of two >= 2 * max_points.
 __device__ __forceinline__ int hs_hash_slot(int cell, int log2_size) { return (int)(((unsigned)cell * 2654435761u) >> (32 - log2_size)); }
 
@@ -639,9 +649,16 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS) k_raycast(HsParams P, int 
   __shared__ unsigned long long s_alloc;   // walk-list allocator: owners << 32 | segments
   __shared__ unsigned s_visits;
 
-  int slot = blockIdx.x / P.n_levels;
-  int level = blockIdx.x - slot * P.n_levels;
+  // slot-major launch order: the long fine-grid CTAs and the short coarse-grid CTAs of a scan are dispatched together, which
+  // keeps the mix of shared-memory-bound (walk) and HBM-bound (sweep) work on every SM even (measured: level-major order
+  // is 20 % slower)
+  int level, slot;
+  {
+    slot = blockIdx.x / P.n_levels;
+    level = blockIdx.x - slot * P.n_levels;
+  }
   if (slot >= n_slots) return;
+  hs_stamp(P, 0);
   if (!P.slot_integrate[slot]) return;
   int s = hs_slot_stream(stream_ids, slot);
   const HsLevel& L = P.lv[level];
@@ -680,7 +697,14 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS) k_raycast(HsParams P, int 
   const int lane = threadIdx.x & 31;
 
   // clear the hash table, reset the box and the allocators
-  for (int i = threadIdx.x; i < hash_size; i += T) { hkeys[i] = HS_HASH_EMPTY; hvals[i] = INT_MAX; }
+  {
+    int4* k4 = reinterpret_cast<int4*>(hkeys);
+    int4* v4 = reinterpret_cast<int4*>(hvals);
+    for (int i = threadIdx.x; i < (hash_size >> 2); i += T) {
+      k4[i] = make_int4(HS_HASH_EMPTY, HS_HASH_EMPTY, HS_HASH_EMPTY, HS_HASH_EMPTY);
+      v4[i] = make_int4(INT_MAX, INT_MAX, INT_MAX, INT_MAX);
+    }
+  }
   if (threadIdx.x == 0) { s_box[0] = INT_MAX; s_box[1] = INT_MAX; s_box[2] = INT_MIN; s_box[3] = INT_MIN; s_alloc = 0ULL; s_visits = 0u; }
   __syncthreads();
 
@@ -728,6 +752,7 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS) k_raycast(HsParams P, int 
     __syncthreads();
   }
 
+  hs_stamp(P, 1);
   // phase A2: end point ownership -- io = smallest beam index per end cell
   for (int i = threadIdx.x; i < n; i += T) {
     const HsBeamRec r = beams[i];
@@ -790,6 +815,7 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS) k_raycast(HsParams P, int 
     }
   }
   __syncthreads();
+  hs_stamp(P, 2);
   const int n_walk = (int)(s_alloc >> 32), n_items = (int)(unsigned)(s_alloc & 0xFFFFFFFFULL);
 
   // phase B1: free cells with the reference's bresenham2D recurrence (OccGridMapBase.h:243-260). Every thread takes
@@ -798,11 +824,14 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS) k_raycast(HsParams P, int 
   //   cell(t) = k0 + t*off_a + floor((abs_da/2 + t*abs_db) / abs_da) * off_b,  err(t) = (abs_da/2 + t*abs_db) mod abs_da.
   // Marks go to the 2-bit-per-cell map of the bounding box in SHARED memory: the ~49 k scattered cell visits of a scan
   // never reach L2/HBM.
-  if (use_map) {
+  if (P.dbg_skip & 1) {
+  } else if (use_map) {
     const int k0 = (by - y0) * pitch + (bx - x0);
     const unsigned cmap_s = hs_shared_addr(cmap);
     const int per = (n_items + T - 1) / T;
-    int j = threadIdx.x * per;
+    // neighbouring lanes take segments ~37 beams apart: lanes that walk adjacent beams at the same radius would hit
+    // the same 16-cell map words in the same instruction and serialise in the shared-memory atomics
+    int j = (int)((threadIdx.x * 37u) % (unsigned)T) * per;
     const int j1 = min(j + per, n_items);
     if (j < j1) {
       int lo = 0, hi = n_walk - 1;       // largest p with walk[p].seg_start <= j
@@ -871,30 +900,34 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS) k_raycast(HsParams P, int 
   }
   __syncthreads();
 
+  hs_stamp(P, 3);
   // phase B2: updateSetFree exactly once per marked cell -- coalesced sweep of the bounding box.
   const bool vec_ok = use_map && ((W & 3) == 0) && ((reinterpret_cast<uintptr_t>(val) & 15) == 0);
-  if (vec_ok) {
+  if (P.dbg_skip & 2) {
+  } else if (vec_ok) {
     // fast path: the box is a list of aligned 4-cell quads (one float4 of log-odds, 4 map bits), dealt out to the threads
-    // in row-major order, four quads in flight per thread. Unmarked components are written back unchanged, hence the
-    // barrier before phase C touches the end cells.
+    // in row-major order (a warp's 32 quads are 512 contiguous bytes of a row), four quads in flight per thread.
+    // Unmarked components are written back unchanged, hence the barrier before phase C touches the end cells.
     const int qpr = ((x1 - x0) >> 2) + 1;     // quads per box row (x0 is 32-aligned, W a multiple of 4)
     const int nq = qpr * bh;
     const int4 mf4 = make_int4(mark_free, mark_free, mark_free, mark_free);
+    const int d_ry = T / qpr, d_c = T - d_ry * qpr;   // one stride of T quads, as (rows, quads)
+    int c;
+    int ry = hs_udiv_small(threadIdx.x, qpr, c);
     for (int q0 = threadIdx.x; q0 < nq; q0 += 4 * T) {
       unsigned bits[4];
       int g[4];
       float4 v[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int q = q0 + u * T;
         bits[u] = 0u;
-        if (q < nq) {
-          int c;
-          const int ry = hs_udiv_small(q, qpr, c);
+        if (q0 + u * T < nq) {
           bits[u] = (cmap[ry * pw + (c >> 2)] >> ((unsigned)(c & 3) << 2)) & 0xFu;
           g[u] = (y0 + ry) * W + x0 + (c << 2);
           if (bits[u]) v[u] = *reinterpret_cast<const float4*>(val + g[u]);
         }
+        ry += d_ry; c += d_c;
+        if (c >= qpr) { c -= qpr; ++ry; }
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -949,9 +982,10 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS) k_raycast(HsParams P, int 
     }
   }
 
+  hs_stamp(P, 4);
   // phase C: end points -- the owner beam applies undo-free / occupied and stores markOcc
   // (end cells are disjoint from the cells B2 marks: their free bit / free marker is never set)
-  for (int wi = threadIdx.x; wi < n_walk; wi += T) {
+  for (int wi = threadIdx.x; wi < ((P.dbg_skip & 4) ? 0 : n_walk); wi += T) {
     const int i = walk[wi].beam;
     const int kend = beams[i].kend;
     const int h = hs_hash_find(hkeys, hash_mask, log2_hash, kend);
@@ -962,6 +996,8 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS) k_raycast(HsParams P, int 
     val[kend] = v;
     idx[kend] = mark_occ;
   }
+  __syncthreads();
+  hs_stamp(P, 5);
 }
 
 // ------------------------------------------------------------------------------------------------
