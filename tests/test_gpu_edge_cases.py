@@ -1,6 +1,6 @@
 """GPU edge cases against the CPU oracle, bit for bit: empty and ragged scans, beams leaving the map, pose hints,
 map_without_matching (stale coarse containers), reset, stream subsets via stream_ids, the LaserScan-ranges entry
-point, the large-bounding-box fallback of the ray-caster, map upload/download/classification, and the
+point, band-wise ray-casting of large bounding boxes, map upload/download/classification, and the
 size-independent properties used at BASELINE sizes."""
 import numpy as np
 import pytest
@@ -125,9 +125,9 @@ def test_ranges_entry_point_equals_points_entry_point(hs, oracle):
     eng.close()
 
 
-def test_large_bounding_box_uses_global_fallback(hs, oracle):
-    """Scans whose bounding box exceeds the shared-memory cell map (here: a 2048^2 @0.01 m grid, box ~1000^2 cells)
-    take the ray-caster's global-marker path; results stay bit-exact."""
+def test_large_bounding_box_is_processed_in_bands(hs, oracle):
+    """Scans whose bounding box exceeds the shared-memory cell map (here: a 2048^2 @0.01 m grid, box ~1000^2 cells,
+    i.e. ~6 bands of rows on level 0) are ray-cast band by band; results stay bit-exact."""
     n, n_scans = 2, 6
     sc, ranges, pts, cnt, truth = make_streams(hs, n, n_scans, seed0=1234, scale_to_map=100.0)
     eng, procs = setup_pair(hs, oracle, n, size=2048, levels=2, res=0.01)
@@ -138,6 +138,37 @@ def test_large_bounding_box_uses_global_fallback(hs, oracle):
             assert np.array_equal(bits(out[s]), bits(ref)), (k, s)
     assert_same_maps(eng, procs, 2)
     eng.close()
+
+
+def test_teacher_forced_bands_all_octants(hs, oracle):
+    """Teacher-forced integration of hand-made scans on a 4096^2 grid: long beams in every octant (incl. axis-parallel and
+    exactly diagonal ones, shared end cells and beams leaving the grid) from several start cells, so that every band of the
+    box sees x- and y-dominant traces entering and leaving it. Markers and log-odds bits must equal the CPU oracle's."""
+    size, res, mp = 4096, 0.025, 256
+    rng = np.random.default_rng(5)
+    n = 4
+    ang = np.linspace(0.0, 2.0 * np.pi, 200, endpoint=False)
+    pts = np.zeros((n, mp, 2), np.float32)
+    cnt = np.zeros(n, np.int32)
+    for s in range(n):
+        rad = rng.uniform(30.0, 1900.0, ang.size) if s < 3 else np.full(ang.size, 1200.0)
+        p = np.stack([np.cos(ang) * rad, np.sin(ang) * rad], 1)
+        extra = np.array([[1500, 0], [-1500, 0], [0, 1500], [0, -1500], [1000, 1000], [-1000, 1000], [1000, -1000], [-1000, -1000],
+                          [1000, 1000], [3000, 10], [10, -3000], [0.2, 0.1], [1, 0]], np.float32)
+        p = np.concatenate([p, extra]).astype(np.float32)
+        pts[s, :len(p)] = p
+        cnt[s] = len(p)
+    poses = np.array([[0, 0, 0], [3.3, -2.1, 0.7], [-11.0, 7.5, -2.9], [0.01, 0.02, 3.1]], np.float32)
+    origos = np.array([[0, 0], [4.0, -2.5], [0, 0], [-7.5, 3.25]], np.float32)
+    with hs.Engine(res, size, size, (0.5, 0.5), 3, n_streams=n, max_points=mp) as eng:
+        procs = [oracle.CpuProcessor("port", res, size, size, (0.5, 0.5), 3) for _ in range(n)]
+        for rep in range(2):
+            eng.raycast_batch(pts, cnt, poses, origos=origos)
+            for s, p in enumerate(procs):
+                p.raycast(pts[s], poses[s], n=int(cnt[s]), origo=origos[s])
+        assert_same_maps(eng, procs, 3)
+        for p in procs:
+            p.close()
 
 
 def test_upload_download_classify_roundtrip(hs):

@@ -94,7 +94,7 @@ static int raycast_log2_hash(int max_points) {
   return l;
 }
 static size_t raycast_smem_for(int max_points) {
-  return (size_t)HS_MAP_BYTES + 2 * sizeof(int) * ((size_t)1 << raycast_log2_hash(max_points)) + (size_t)max_points * sizeof(HsWalkRec) + (size_t)max_points * sizeof(HsBeamRec) + 16;
+  return (size_t)HS_MAP_BYTES + 2 * sizeof(int) * ((size_t)1 << raycast_log2_hash(max_points)) + (size_t)max_points * sizeof(HsWalkRec) + (size_t)max_points * sizeof(HsBeamRec) + 2 * (size_t)max_points * sizeof(unsigned short) + 16;
 }
 static size_t raycast_smem(const hs_engine* e) { return raycast_smem_for(e->P.max_points); }
 static int warp_grid(int n_warps, int threads) { return (n_warps * 32 + threads - 1) / threads; }
@@ -155,7 +155,7 @@ int hs_create(const hs_config* cfg, hs_engine** out) {
   if (!cfg || !out) return HS_ERR_INVALID_ARG;
   *out = nullptr;
   if (cfg->levels < 1 || cfg->levels > HS_MAX_LEVELS || cfg->n_streams < 1 || cfg->max_points < 1 || cfg->max_points > 5600 ||
-      cfg->map_size_x < 2 || cfg->map_size_y < 2 || !(cfg->map_resolution > 0.0f))
+      cfg->map_size_x < 2 || cfg->map_size_y < 2 || cfg->map_size_x > 16384 || cfg->map_size_y > 16384 || !(cfg->map_resolution > 0.0f))
     return HS_ERR_INVALID_ARG;
   if ((cfg->map_size_x >> (cfg->levels - 1)) < 2 || (cfg->map_size_y >> (cfg->levels - 1)) < 2) return HS_ERR_INVALID_ARG;
   int n_dev = 0;

@@ -18,6 +18,8 @@
 #include <float.h>
 #include <limits.h>
 
+#include <type_traits>
+
 #include "hs_libm_exact.h"
 #include "hsgpu.h"
 
@@ -569,8 +571,8 @@ struct HsBeamRec {
 struct __align__(16) HsWalkRec {
   unsigned dadb;               // abs_da | abs_db << 16
   unsigned offs;               // cell-address step along the dominant axis (low 16 bits, signed) | along the minor axis << 16
-  int beam;                    // beam index (the reference's loop position; decides "free came first")
-  int seg_start;               // index of this beam's first walk segment (ascending over the walk list)
+  int beam;                    // beam index (the reference's loop position; decides "free came first") | x-dominant << 30 | y grows << 31
+  int seg_start;               // index of this beam's first walk segment in the current band (ascending over the walk list)
 };
 
 // exact x / d for 0 <= x < 2^22, 0 < d < 2^22: approximate float quotient (MUFU.RCP, <= 2 ulp) + one-step correction
@@ -632,10 +634,10 @@ __device__ __forceinline__ void hs_free_hits_end_cell(const int* __restrict__ hk
 }
 
 // dynamic shared memory: HS_MAP_BYTES (cell map) | hash keys[T] | hash vals[T] | max_points * sizeof(HsWalkRec)
-// | max_points * sizeof(HsBeamRec), T = hash_size (power of two >= 2 * max_points).
+// | max_points * sizeof(HsBeamRec) | 2 * max_points * sizeof(unsigned short), T = hash_size (power of two >= 2 * max_points).
 // log2_seg_levels: the free-cell walk is cut into segments of 2^k steps that are dealt out evenly to the threads
 // (k = low byte on level 0, next byte on the coarser levels).
-__global__ void __launch_bounds__(HS_RAYCAST_THREADS) k_raycast(HsParams P, int n_slots, const int32_t* __restrict__ stream_ids,
+__global__ void __launch_bounds__(HS_RAYCAST_THREADS, 3) k_raycast(HsParams P, int n_slots, const int32_t* __restrict__ stream_ids,
                                                                 const float2* __restrict__ points, const int32_t* __restrict__ counts,
                                                                 const float2* __restrict__ origos, int log2_hash, int log2_seg_levels) {
   extern __shared__ __align__(16) unsigned char hs_smem[];
@@ -645,8 +647,12 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS) k_raycast(HsParams P, int 
   int* hvals = hkeys + hash_size;                                          // (io << 1) | free-came-first flag
   HsWalkRec* walk = reinterpret_cast<HsWalkRec*>(hvals + hash_size);       // owner beams
   HsBeamRec* beams = reinterpret_cast<HsBeamRec*>(walk + P.max_points);
+  unsigned short* tlo = reinterpret_cast<unsigned short*>(beams + P.max_points);   // per owner: first step inside the current band
+  unsigned short* tlen = tlo + P.max_points;                                        // ... and the number of steps inside it
   __shared__ int s_box[4];  // xmin, ymin, xmax, ymax over the start cell and all valid end cells
-  __shared__ unsigned long long s_alloc;   // walk-list allocator: owners << 32 | segments
+  __shared__ unsigned long long s_alloc;   // walk-list allocator: owners << 32 | segments (single band)
+  __shared__ int s_items;
+  __shared__ int s_wsum[32];
   __shared__ unsigned s_visits;
 
   // slot-major launch order: the long fine-grid CTAs and the short coarse-grid CTAs of a scan are dispatched together, which
@@ -739,17 +745,22 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS) k_raycast(HsParams P, int 
   if (threadIdx.x == 0) atomicAdd(&P.counters[3], (unsigned long long)s_visits);
 
   // geometry of the cell map: rows of `pitch` cells starting at a 32-aligned x0; the row pitch in words is odd so
-  // that a vertical run of cells spreads over the shared-memory banks
+  // that a vertical run of cells spreads over the shared-memory banks. A box with more cells than the map holds is
+  // processed in horizontal bands of `band_rows` rows, one after the other (hi-res grids, long ranges).
   const int x0 = s_box[0] & ~31, y0 = s_box[1], x1 = s_box[2], y1 = s_box[3];
   const int bh = y1 - y0 + 1;
   const int pw = (((x1 - x0) >> 4) + 1) | 1;   // 16-cell words per map row
   const int pitch = pw << 4;                   // cells per map row
-  const bool use_map = (long long)pitch * bh <= HS_MAP_CELLS;
-  if (use_map) {   // clear the part of the cell map this scan uses
+  const int band_rows = min(bh, HS_MAP_CELLS / pitch);   // >= 1: hs_create limits the grid width
+  const int n_bands = (bh + band_rows - 1) / band_rows;
+
+  const bool single_band = n_bands == 1;
+  const int log2_seg = level == 0 ? (log2_seg_levels & 0xFF) : (log2_seg_levels >> 8);   // per level: fine grid / coarse grids
+  const int seg = 1 << log2_seg;
+  if (single_band) {   // clear the part of the cell map this scan uses (A3 sets the end bits after A2's barrier)
     uint4* m4 = reinterpret_cast<uint4*>(hs_smem);
     const int n4 = (pw * bh + 3) >> 2;
     for (int i = threadIdx.x; i < n4; i += T) m4[i] = make_uint4(0u, 0u, 0u, 0u);
-    __syncthreads();
   }
 
   hs_stamp(P, 1);
@@ -764,21 +775,11 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS) k_raycast(HsParams P, int 
       h = (h + 1) & hash_mask;
     }
     atomicMin(&hvals[h], i << 1);
-    if (use_map) {
-      int ey = r.kend / W, ex = r.kend - ey * W;
-      int kb = (ey - y0) * pitch + (ex - x0);
-      atomicOr(&cmap[kb >> 4], 0x10000u << (kb & 15));
-    }
   }
   __syncthreads();
 
   // phase A3: walk list = the owner beam of every end cell. Beams that share an end cell have identical traces (same
   // start, same end), and the owner -- the smallest index -- is the one that decides every "free came first" question.
-  // Each owner's trace is cut into segments of `seg` steps; one 64-bit shared atomicAdd per warp hands out list
-  // positions and segment indices together, so seg_start ascends along the list.
-  const int log2_seg = level == 0 ? (log2_seg_levels & 0xFF) : (log2_seg_levels >> 8);   // per level: fine grid / coarse grids
-  const int seg = 1 << log2_seg;
-  const int row_step = use_map ? pitch : W;                       // address step of one cell in y
   for (int i0 = 0; i0 < n; i0 += T) {
     const int i = i0 + threadIdx.x;
     bool owner = false;
@@ -791,12 +792,16 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS) k_raycast(HsParams P, int 
         owner = (hvals[h] >> 1) == i;
       }
     }
-    const int nseg = owner ? ((int)r.da + seg - 1) >> log2_seg : 0;
+    // one 64-bit shared atomicAdd per warp hands out list positions and (single band) segment indices together, so
+    // seg_start ascends along the list
+    const int nseg = (owner && single_band) ? ((int)r.da + seg - 1) >> log2_seg : 0;
     int incl = nseg;
+    if (single_band) {
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      int t = __shfl_up_sync(0xffffffffu, incl, d);
-      if (lane >= d) incl += t;
+      for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+      }
     }
     const unsigned m = __ballot_sync(0xffffffffu, owner);
     unsigned long long base = 0ULL;
@@ -804,189 +809,243 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS) k_raycast(HsParams P, int 
     base = __shfl_sync(0xffffffffu, base, 31);
     if (owner) {
       const int sa = (r.flags & 2) ? 1 : -1, sb = (r.flags & 4) ? 1 : -1;
-      const int off_a = (r.flags & 1) ? sa : sa * row_step;
-      const int off_b = (r.flags & 1) ? sb * row_step : sb;
+      const int off_a = (r.flags & 1) ? sa : sa * pitch;
+      const int off_b = (r.flags & 1) ? sb * pitch : sb;
       HsWalkRec w;
       w.dadb = (unsigned)r.da | ((unsigned)r.db << 16);
       w.offs = ((unsigned)off_a & 0xFFFFu) | ((unsigned)off_b << 16);
-      w.beam = i;
+      const unsigned xdom = r.flags & 1u;   // y grows along the trace: sign of the minor step (x-dominant) or of the major step
+      const unsigned y_up = xdom ? ((r.flags >> 2) & 1u) : ((r.flags >> 1) & 1u);
+      w.beam = (int)((unsigned)i | (xdom << 30) | (y_up << 31));
       w.seg_start = (int)(unsigned)(base & 0xFFFFFFFFULL) + incl - nseg;
-      walk[(int)(base >> 32) + __popc(m & ((1u << lane) - 1u))] = w;
+      const int pos = (int)(base >> 32) + __popc(m & ((1u << lane) - 1u));
+      walk[pos] = w;
+      if (single_band) {   // the whole trace lies in the one band; mark the end cell in the (already cleared) map
+        tlo[pos] = 0;
+        tlen[pos] = r.da;
+        const int ey = r.kend / W, ex = r.kend - ey * W;
+        const int kb = (ey - y0) * pitch + (ex - x0);
+        atomicOr(&cmap[kb >> 4], 0x10000u << (kb & 15));
+      }
     }
   }
   __syncthreads();
+  const int n_walk = (int)(s_alloc >> 32);
   hs_stamp(P, 2);
-  const int n_walk = (int)(s_alloc >> 32), n_items = (int)(unsigned)(s_alloc & 0xFFFFFFFFULL);
 
-  // phase B1: free cells with the reference's bresenham2D recurrence (OccGridMapBase.h:243-260). Every thread takes
-  // the same number of consecutive walk segments (so the longest beam no longer sets the CTA's pace); a thread that
-  // starts inside a beam enters the recurrence through its closed form after t steps:
-  //   cell(t) = k0 + t*off_a + floor((abs_da/2 + t*abs_db) / abs_da) * off_b,  err(t) = (abs_da/2 + t*abs_db) mod abs_da.
-  // Marks go to the 2-bit-per-cell map of the bounding box in SHARED memory: the ~49 k scattered cell visits of a scan
-  // never reach L2/HBM.
-  if (P.dbg_skip & 1) {
-  } else if (use_map) {
-    const int k0 = (by - y0) * pitch + (bx - x0);
-    const unsigned cmap_s = hs_shared_addr(cmap);
-    const int per = (n_items + T - 1) / T;
-    // neighbouring lanes take segments ~37 beams apart: lanes that walk adjacent beams at the same radius would hit
-    // the same 16-cell map words in the same instruction and serialise in the shared-memory atomics
-    int j = (int)((threadIdx.x * 37u) % (unsigned)T) * per;
-    const int j1 = min(j + per, n_items);
-    if (j < j1) {
-      int lo = 0, hi = n_walk - 1;       // largest p with walk[p].seg_start <= j
-      while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (walk[mid].seg_start <= j) lo = mid; else hi = mid - 1;
-      }
-      int p = lo;
-      HsWalkRec w = walk[p];
-      int da = (int)(w.dadb & 0xFFFFu), db = (int)(w.dadb >> 16);
-      int off_a = (int)(short)(w.offs & 0xFFFFu), off_b = ((int)w.offs) >> 16;
-      int beam = w.beam;
-      const int t0 = (j - w.seg_start) << log2_seg;
-      const int e0 = (da >> 1) + t0 * db;
-      const int q0 = e0 / da;
-      int k = k0 + t0 * off_a + q0 * off_b, err = e0 - q0 * da, rem = da - t0;
-      for (; j < j1; ++j) {
-        const int steps = min(seg, rem);
-        for (int t = 0; t < steps; ++t) {
-          const unsigned waddr = cmap_s + (((unsigned)k >> 4) << 2);
-          const unsigned word = hs_lds_u32(waddr);
-          const unsigned mbit = 0x10001u << ((unsigned)k & 15u);
-          const unsigned hit = word & mbit;
-          if (hit == 0u) {
-            hs_reds_or(waddr, mbit & 0xFFFFu);
-          } else if (hit & 0xFFFF0000u) {   // the free trace crosses a cell that is some beam's end point
-            const int yy = k / pitch, xx = k - yy * pitch;
-            hs_free_hits_end_cell(hkeys, hvals, hash_mask, log2_hash, (yy + y0) * W + (xx + x0), beam);
+  const int warp = threadIdx.x >> 5, n_warps = T >> 5;
+  const bool vec_ok = ((W & 3) == 0) && ((reinterpret_cast<uintptr_t>(val) & 15) == 0);
+  const unsigned cmap_s = hs_shared_addr(cmap);
+
+  auto run_bands = [&](auto single_c) {
+  constexpr bool SINGLE = decltype(single_c)::value;
+  for (int band = 0; band < (SINGLE ? 1 : n_bands); ++band) {
+    const int yb0 = SINGLE ? y0 : y0 + band * band_rows;
+    const int rows = SINGLE ? bh : min(band_rows, y1 - yb0 + 1);
+    const int yb1 = yb0 + rows - 1;
+    if (!SINGLE) {   // clear the part of the cell map this band uses
+      uint4* m4 = reinterpret_cast<uint4*>(hs_smem);
+      const int n4 = (pw * rows + 3) >> 2;
+      for (int i = threadIdx.x; i < n4; i += T) m4[i] = make_uint4(0u, 0u, 0u, 0u);
+      if (threadIdx.x == 0) s_items = 0;
+    }
+    if (!SINGLE) __syncthreads();
+
+    // per owner: end bit of its end cell, the steps [t_lo, t_lo + len) of its trace that lie in this band (a trace is
+    // monotone in y), cut into segments of `seg` steps; seg_start = exclusive prefix sum over the walk list
+    for (int w0 = 0; w0 < (SINGLE ? 0 : n_walk); w0 += T) {
+      const int wi = w0 + threadIdx.x;
+      int nseg = 0;
+      if (wi < n_walk) {
+        const HsWalkRec w = walk[wi];
+        const int da = (int)(w.dadb & 0xFFFFu), db = (int)(w.dadb >> 16);
+        const int kend = beams[w.beam & 0x3FFFFFFF].kend;
+        const int ey = kend / W, ex = kend - ey * W;
+        if (ey >= yb0 && ey <= yb1) {
+          const int kb = (ey - yb0) * pitch + (ex - x0);
+          atomicOr(&cmap[kb >> 4], 0x10000u << (kb & 15));
+        }
+        int t_lo = 0, t_hi = da - 1;
+        {
+          const bool y_up = (w.beam >> 31) & 1;
+          // rows of the band in units of "y steps from the start cell along the trace"
+          int r_lo = y_up ? yb0 - by : by - yb1, r_hi = y_up ? yb1 - by : by - yb0;
+          if (w.beam & 0x40000000) {   // x-dominant: row(t) = floor((da/2 + t*db) / da)
+            const int half = da >> 1;
+            const int r_max = (half + (da - 1) * db) / da;
+            if (r_lo > r_max || r_hi < 0) { t_hi = -1; }
+            else {
+              if (r_lo > 0) t_lo = (r_lo * da - half + db - 1) / db;                 // db > 0 here (r_max >= r_lo > 0)
+              if (r_hi < r_max) t_hi = ((r_hi + 1) * da - half + db - 1) / db - 1;
+            }
+          } else {                     // y-dominant: row(t) = t
+            t_lo = max(r_lo, 0);
+            t_hi = min(r_hi, da - 1);
           }
-          k += off_a;
-          err += db;
-          if (err >= da) { k += off_b; err -= da; }
         }
-        rem -= steps;
-        if (rem == 0 && j + 1 < j1) {
-          w = walk[++p];
-          da = (int)(w.dadb & 0xFFFFu); db = (int)(w.dadb >> 16);
-          off_a = (int)(short)(w.offs & 0xFFFFu); off_b = ((int)w.offs) >> 16;
-          beam = w.beam;
-          k = k0; err = da >> 1; rem = da;
-        }
+        const int len = t_hi >= t_lo ? t_hi - t_lo + 1 : 0;
+        tlo[wi] = (unsigned short)t_lo;
+        tlen[wi] = (unsigned short)len;
+        nseg = (len + seg - 1) >> log2_seg;
       }
-    }
-  } else {
-    // the bounding box does not fit the cell map: mark in the global marker plane (idx = markFree by plain,
-    // idempotent stores); one thread per owner beam
-    const int k0 = by * W + bx;
-    for (int wi = threadIdx.x; wi < n_walk; wi += T) {
-      const HsWalkRec w = walk[wi];
-      const int da = (int)(w.dadb & 0xFFFFu), db = (int)(w.dadb >> 16);
-      const int off_a = (int)(short)(w.offs & 0xFFFFu), off_b = ((int)w.offs) >> 16;
-      int k = k0, err = da >> 1;
-      for (int t = 0; t < da; ++t) {
-        int h = hs_hash_find(hkeys, hash_mask, log2_hash, k);
-        if (h >= 0) {                 // end cell: only the "free came first" flag matters
-          int hv = hvals[h];
-          if (w.beam < (hv >> 1) && !(hv & 1)) atomicOr(&hvals[h], 1);
-        } else if (idx[k] < mark_free) {  // may be served by L1: a stale "not yet marked" only repeats an idempotent store
-          idx[k] = mark_free;
-        }
-        k += off_a;
-        err += db;
-        if (err >= da) { k += off_b; err -= da; }
+      int incl = nseg;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
       }
+      if (lane == 31) s_wsum[warp] = incl;
+      __syncthreads();
+      int off = s_items;
+      for (int k = 0; k < warp; ++k) off += s_wsum[k];
+      if (wi < n_walk) walk[wi].seg_start = off + incl - nseg;
+      __syncthreads();
+      if (threadIdx.x == T - 1) s_items = off + incl;
     }
-  }
-  __syncthreads();
+    if (!SINGLE) __syncthreads();
+    const int n_items = SINGLE ? (int)(unsigned)(s_alloc & 0xFFFFFFFFULL) : s_items;
 
-  hs_stamp(P, 3);
-  // phase B2: updateSetFree exactly once per marked cell -- coalesced sweep of the bounding box.
-  const bool vec_ok = use_map && ((W & 3) == 0) && ((reinterpret_cast<uintptr_t>(val) & 15) == 0);
-  if (P.dbg_skip & 2) {
-  } else if (vec_ok) {
-    // fast path: the box is a list of aligned 4-cell quads (one float4 of log-odds, 4 map bits), dealt out to the threads
-    // in row-major order (a warp's 32 quads are 512 contiguous bytes of a row), four quads in flight per thread.
-    // Unmarked components are written back unchanged, hence the barrier before phase C touches the end cells.
-    const int qpr = ((x1 - x0) >> 2) + 1;     // quads per box row (x0 is 32-aligned, W a multiple of 4)
-    const int nq = qpr * bh;
-    const int4 mf4 = make_int4(mark_free, mark_free, mark_free, mark_free);
-    const int d_ry = T / qpr, d_c = T - d_ry * qpr;   // one stride of T quads, as (rows, quads)
-    int c;
-    int ry = hs_udiv_small(threadIdx.x, qpr, c);
-    for (int q0 = threadIdx.x; q0 < nq; q0 += 4 * T) {
-      unsigned bits[4];
-      int g[4];
-      float4 v[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        bits[u] = 0u;
-        if (q0 + u * T < nq) {
-          bits[u] = (cmap[ry * pw + (c >> 2)] >> ((unsigned)(c & 3) << 2)) & 0xFu;
-          g[u] = (y0 + ry) * W + x0 + (c << 2);
-          if (bits[u]) v[u] = *reinterpret_cast<const float4*>(val + g[u]);
+    // phase B1: free cells with the reference's bresenham2D recurrence (OccGridMapBase.h:243-260). Every thread takes
+    // the same number of consecutive walk segments (so the longest beam does not set the CTA's pace); a thread that
+    // starts inside a beam enters the recurrence through its closed form after t steps:
+    //   cell(t) = k0 + t*off_a + floor((abs_da/2 + t*abs_db) / abs_da) * off_b,  err(t) = (abs_da/2 + t*abs_db) mod abs_da.
+    // Marks go to the 2-bit-per-cell map of the band in SHARED memory: the scattered cell visits of a scan never reach
+    // L2/HBM.
+    if (!(P.dbg_skip & 1)) {
+      const int k0 = (by - yb0) * pitch + (bx - x0);   // map address of the start cell (may lie outside this band)
+      const int per = (n_items + T - 1) / T;
+      // neighbouring lanes take segments ~37 beams apart: lanes that walk adjacent beams at the same radius would hit
+      // the same 16-cell map words in the same instruction and serialise in the shared-memory atomics
+      int j = (int)((threadIdx.x * 37u) % (unsigned)T) * per;
+      const int j1 = min(j + per, n_items);
+      if (j < j1) {
+        int lo = 0, hi = n_walk - 1;       // largest p with walk[p].seg_start <= j
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if (walk[mid].seg_start <= j) lo = mid; else hi = mid - 1;
         }
-        ry += d_ry; c += d_c;
-        if (c >= qpr) { c -= qpr; ++ry; }
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (bits[u]) {
-          float4 w = v[u];
-          if (bits[u] & 1u) w.x = w.x + f;
-          if (bits[u] & 2u) w.y = w.y + f;
-          if (bits[u] & 4u) w.z = w.z + f;
-          if (bits[u] & 8u) w.w = w.w + f;
-          *reinterpret_cast<float4*>(val + g[u]) = w;
-          if (bits[u] == 0xFu) {
-            *reinterpret_cast<int4*>(idx + g[u]) = mf4;
-          } else {
-            if (bits[u] & 1u) idx[g[u]] = mark_free;
-            if (bits[u] & 2u) idx[g[u] + 1] = mark_free;
-            if (bits[u] & 4u) idx[g[u] + 2] = mark_free;
-            if (bits[u] & 8u) idx[g[u] + 3] = mark_free;
+        int p = lo;
+        HsWalkRec w = walk[p];
+        int da = (int)(w.dadb & 0xFFFFu), db = (int)(w.dadb >> 16);
+        int off_a = (int)(short)(w.offs & 0xFFFFu), off_b = ((int)w.offs) >> 16;
+        int beam = w.beam & 0x3FFFFFFF;
+        const int s_off = (j - w.seg_start) << log2_seg;
+        int t0 = (SINGLE ? 0 : (int)tlo[p]) + s_off;
+        int rem = (SINGLE ? da : (int)tlen[p]) - s_off;
+        int e0 = (da >> 1) + t0 * db;
+        int q0 = e0 / da;
+        int k = k0 + t0 * off_a + q0 * off_b, err = e0 - q0 * da;
+        for (; j < j1; ++j) {
+          const int steps = min(seg, rem);
+          for (int t = 0; t < steps; ++t) {
+            const unsigned waddr = cmap_s + (((unsigned)k >> 4) << 2);
+            const unsigned word = hs_lds_u32(waddr);
+            const unsigned mbit = 0x10001u << ((unsigned)k & 15u);
+            const unsigned hit = word & mbit;
+            if (hit == 0u) {
+              hs_reds_or(waddr, mbit & 0xFFFFu);
+            } else if (hit & 0xFFFF0000u) {   // the free trace crosses a cell that is some beam's end point
+              const int yy = k / pitch, xx = k - yy * pitch;
+              hs_free_hits_end_cell(hkeys, hvals, hash_mask, log2_hash, (yy + yb0) * W + (xx + x0), beam);
+            }
+            k += off_a;
+            err += db;
+            if (err >= da) { k += off_b; err -= da; }
+          }
+          rem -= steps;
+          if (rem == 0 && j + 1 < j1) {
+            if (SINGLE) ++p; else do { ++p; } while (tlen[p] == 0);
+            w = walk[p];
+            da = (int)(w.dadb & 0xFFFFu); db = (int)(w.dadb >> 16);
+            off_a = (int)(short)(w.offs & 0xFFFFu); off_b = ((int)w.offs) >> 16;
+            beam = w.beam & 0x3FFFFFFF;
+            if (SINGLE) {
+              k = k0; err = da >> 1; rem = da;
+            } else {
+              t0 = (int)tlo[p]; rem = (int)tlen[p];
+              e0 = (da >> 1) + t0 * db;
+              q0 = t0 ? e0 / da : 0;
+              k = k0 + t0 * off_a + q0 * off_b; err = e0 - q0 * da;
+            }
           }
         }
       }
     }
     __syncthreads();
-  } else {
-    // generic path (any grid width, and the global-marker fallback): a lane owns one cell per 32-cell segment
-    const int warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-    const int segs = ((x1 - x0) >> 5) + 1;
-    for (int ry = warp; ry < bh; ry += n_warps) {
-      const int row = (y0 + ry) * W + x0 + lane;
-      const unsigned* mrow = cmap + ry * pw + (lane >> 4);
-      for (int sg0 = 0; sg0 < segs; sg0 += 4) {
-        float v[4];
-        bool on[4];
+    if (band == 0) hs_stamp(P, 3);
+
+    // phase B2: updateSetFree exactly once per marked cell -- coalesced sweep of the band.
+    if (P.dbg_skip & 2) {
+    } else if (vec_ok) {
+      // fast path: the band is a list of aligned 4-cell quads (one float4 of log-odds, 4 map bits), dealt out to the
+      // threads in row-major order (a warp's 32 quads are 512 contiguous bytes of a row), four quads in flight per
+      // thread. Unmarked components are written back unchanged, hence the barrier before phase C touches the end cells.
+      const int qpr = ((x1 - x0) >> 2) + 1;     // quads per box row (x0 is 32-aligned, W a multiple of 4)
+      const int nq = qpr * rows;
+      const int4 mf4 = make_int4(mark_free, mark_free, mark_free, mark_free);
+      const int d_ry = T / qpr, d_c = T - d_ry * qpr;   // one stride of T quads, as (rows, quads)
+      int c;
+      int ry = hs_udiv_small(threadIdx.x, qpr, c);
+      for (int q0 = threadIdx.x; q0 < nq; q0 += 4 * T) {
+        unsigned bits[4];
+        int g[4];
+        float4 v[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const int sg = sg0 + u;
-          on[u] = false;
-          if (sg < segs) {
-            const bool inside = x0 + (sg << 5) + lane <= x1;   // the last segment may stick out of the box / map row
-            if (use_map) on[u] = inside && ((mrow[sg * 2] >> (lane & 15)) & 1u);
-            else on[u] = inside && (__ldcg(idx + row + (sg << 5)) == mark_free);
-            if (on[u]) v[u] = val[row + (sg << 5)];
+          bits[u] = 0u;
+          if (q0 + u * T < nq) {
+            bits[u] = (cmap[ry * pw + (c >> 2)] >> ((unsigned)(c & 3) << 2)) & 0xFu;
+            g[u] = (yb0 + ry) * W + x0 + (c << 2);
+            if (bits[u]) v[u] = *reinterpret_cast<const float4*>(val + g[u]);
           }
+          ry += d_ry; c += d_c;
+          if (c >= qpr) { c -= qpr; ++ry; }
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          if (on[u]) {
-            val[row + ((sg0 + u) << 5)] = v[u] + f;
-            if (use_map) idx[row + ((sg0 + u) << 5)] = mark_free;
+          if (bits[u]) {
+            float4 w = v[u];
+            if (bits[u] & 1u) w.x = w.x + f;
+            if (bits[u] & 2u) w.y = w.y + f;
+            if (bits[u] & 4u) w.z = w.z + f;
+            if (bits[u] & 8u) w.w = w.w + f;
+            *reinterpret_cast<float4*>(val + g[u]) = w;
+            if (bits[u] == 0xFu) {
+              *reinterpret_cast<int4*>(idx + g[u]) = mf4;
+            } else {
+              if (bits[u] & 1u) idx[g[u]] = mark_free;
+              if (bits[u] & 2u) idx[g[u] + 1] = mark_free;
+              if (bits[u] & 4u) idx[g[u] + 2] = mark_free;
+              if (bits[u] & 8u) idx[g[u] + 3] = mark_free;
+            }
+          }
+        }
+      }
+    } else {
+      // generic path (any grid width): a lane owns one cell per 32-cell segment
+      const int segs = ((x1 - x0) >> 5) + 1;
+      for (int ry = warp; ry < rows; ry += n_warps) {
+        const int row = (yb0 + ry) * W + x0 + lane;
+        const unsigned* mrow = cmap + ry * pw + (lane >> 4);
+        for (int sg = 0; sg < segs; ++sg) {
+          const bool on = (x0 + (sg << 5) + lane <= x1) && ((mrow[sg * 2] >> (lane & 15)) & 1u);
+          if (on) {
+            val[row + (sg << 5)] = val[row + (sg << 5)] + f;
+            idx[row + (sg << 5)] = mark_free;
           }
         }
       }
     }
+    __syncthreads();   // the map is cleared for the next band / phase C touches cells a quad store may rewrite
   }
+  };
+  if (single_band) run_bands(std::true_type{}); else run_bands(std::false_type{});
 
   hs_stamp(P, 4);
   // phase C: end points -- the owner beam applies undo-free / occupied and stores markOcc
-  // (end cells are disjoint from the cells B2 marks: their free bit / free marker is never set)
+  // (end cells are disjoint from the cells B2 marks: their free bit is never set)
   for (int wi = threadIdx.x; wi < ((P.dbg_skip & 4) ? 0 : n_walk); wi += T) {
-    const int i = walk[wi].beam;
+    const int i = walk[wi].beam & 0x3FFFFFFF;
     const int kend = beams[i].kend;
     const int h = hs_hash_find(hkeys, hash_mask, log2_hash, kend);
     const int hv = hvals[h];
@@ -996,8 +1055,7 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS) k_raycast(HsParams P, int 
     val[kend] = v;
     idx[kend] = mark_occ;
   }
-  __syncthreads();
-  hs_stamp(P, 5);
+  if (P.dbg_times) { __syncthreads(); hs_stamp(P, 5); }
 }
 
 // ------------------------------------------------------------------------------------------------
