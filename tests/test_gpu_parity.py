@@ -132,3 +132,23 @@ def test_closed_loop_fast_tolerance(hs, oracle):
         print("fast mode: worst pose diff", worst, "cells with different marker", n_diff, "max |dlogodds|", max_dv)
         # boundary-flipped end points are reported, not hidden: allow a handful of cells per stream
         assert n_diff <= 4 * n_streams
+
+
+def test_both_matcher_variants_are_bit_identical(hs, oracle, monkeypatch):
+    """k_match (register cache, scans <= 768 points) and k_match2 (shared-memory cache + dense probability pass, longer
+    scans) are the same arithmetic: forced onto the same 360-point streams they must agree with the oracle bit for bit."""
+    n, n_scans = 6, 25
+    sc, ranges, pts, cnt, truth = make_streams(hs, n, n_scans, seed0=77)
+    procs = cpu_streams(oracle, n, dist=0.0, ang=0.0, free=0.4, occ=0.9)
+    ref = np.stack([np.stack([p.update(pts[k, s], cnt[k, s], hint=p.pose()) for s, p in enumerate(procs)]) for k in range(n_scans)])
+    for variant in ("1", "2"):
+        monkeypatch.setenv("HSGPU_MATCH_VARIANT", variant)
+        with hs.Engine(n_streams=n, max_points=360) as eng:
+            configure(eng, dist=0.0, ang=0.0, free=0.4, occ=0.9)
+            for k in range(n_scans):
+                out, cov = eng.update_batch(pts[k], cnt[k])
+                assert np.array_equal(bits(out), bits(ref[k])), (variant, k)
+            n_diff, _ = compare_maps(eng, procs, 3)
+            assert n_diff == 0
+    for p in procs:
+        p.close()

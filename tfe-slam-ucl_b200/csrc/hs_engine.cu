@@ -39,6 +39,8 @@ struct hs_engine {
   // bookkeeping
   uint64_t updates, launches, h2d_bytes, d2h_bytes;
   float free_factor, occ_factor;
+  int match_v2;              // matcher variant: k_match2 (shared-memory cache, dense probability pass) for long scans, k_match
+                             // (register cache) for scans of <= 768 points; HSGPU_MATCH_VARIANT=1|2 overrides
   int log2_seg_levels;       // k_raycast walk segment lengths (log2): level 0 | coarser levels << 8
   // optional per-kernel timing with CUDA events on the launching stream (hs_profile_*)
   int profiling;
@@ -95,6 +97,10 @@ static int raycast_log2_hash(int max_points) {
 }
 static size_t raycast_smem_for(int max_points) {
   return (size_t)HS_MAP_BYTES + 2 * sizeof(int) * ((size_t)1 << raycast_log2_hash(max_points)) + (size_t)max_points * sizeof(HsWalkRec) + (size_t)max_points * sizeof(HsBeamRec) + 2 * (size_t)max_points * sizeof(unsigned short) + 16;
+}
+static size_t match2_smem_for(int max_points) {
+  const size_t pitch = (size_t)(((max_points + 27) & ~31) + 4);   // hs_match2_pitch
+  return HS_NPROD * pitch * sizeof(float) + (size_t)max_points * (sizeof(float4) + sizeof(float2) + sizeof(int) + sizeof(unsigned short)) + 16;
 }
 static size_t raycast_smem(const hs_engine* e) { return raycast_smem_for(e->P.max_points); }
 static int warp_grid(int n_warps, int threads) { return (n_warps * 32 + threads - 1) / threads; }
@@ -269,6 +275,17 @@ int hs_create(const hs_config* cfg, hs_engine** out) {
         return (int)(e1 != cudaSuccess ? e1 : e2);
       }
     }
+    e->match_v2 = cfg->max_points > 768;   // measured on B200: 360 points: k_match 92 us vs k_match2 127 us per 1024 scans; 1440 points: 400 vs 353
+    if (const char* mv = getenv("HSGPU_MATCH_VARIANT")) e->match_v2 = atoi(mv) == 2;
+    int smem2 = (int)match2_smem_for(cfg->max_points);
+    if (smem2 > 48 * 1024) {
+      cudaError_t e4 = cudaFuncSetAttribute(k_match2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
+      cudaError_t e5 = cudaFuncSetAttribute(k_match2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
+      if (e4 != cudaSuccess || e5 != cudaSuccess) {
+        hs_destroy(e);
+        return (int)(e4 != cudaSuccess ? e4 : e5);
+      }
+    }
     int smem_r = (int)raycast_smem_for(cfg->max_points);  // k_raycast's cell map + hash table + beam records
     if (smem_r > 48 * 1024) {
       cudaError_t e3 = cudaFuncSetAttribute(k_raycast, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_r);
@@ -412,10 +429,17 @@ static int check_batch(const hs_engine* e, int n) {
 static int run_update_device(hs_engine* e, int n, const int32_t* ids, const float* points, const int32_t* counts,
                              const float* origos, const float* hints, const uint8_t* flags, int mode) {
   if (n == 0) return HS_OK;
-  const size_t smem = (size_t)e->P.max_points * HS_NPROD * sizeof(float);
   {
     ProfScope ps(e, HS_K_MATCH);
     const int threads = HS_MATCH_THREADS;
+    if (e->match_v2) {
+      const size_t smem2 = match2_smem_for(e->P.max_points);
+      if (e->P.strict)
+        k_match2<true><<<n, threads, smem2, e->stream>>>(e->P, n, ids, (const float2*)points, counts, (const float2*)origos, hints, flags, mode);
+      else
+        k_match2<false><<<n, threads, smem2, e->stream>>>(e->P, n, ids, (const float2*)points, counts, (const float2*)origos, hints, flags, mode);
+    } else {
+    const size_t smem = (size_t)e->P.max_points * HS_NPROD * sizeof(float);
     int ppt = (e->P.max_points + threads - 1) / threads;   // register-resident points (+ cell caches) per thread
     ppt = ppt <= 2 ? 2 : (ppt <= 3 ? 3 : (ppt <= 6 ? 6 : 0));
 #define HS_LAUNCH_MATCH(STRICT_, PPT_)                                                               \
@@ -431,6 +455,7 @@ static int run_update_device(hs_engine* e, int n, const int32_t* ids, const floa
     if (e->P.strict) HS_LAUNCH_MATCH_S(true); else HS_LAUNCH_MATCH_S(false);
 #undef HS_LAUNCH_MATCH_S
 #undef HS_LAUNCH_MATCH
+    }
   }
   HS_LAUNCHED(e);
   if (mode == 0) {

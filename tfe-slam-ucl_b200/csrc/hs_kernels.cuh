@@ -203,6 +203,22 @@ __device__ __forceinline__ void hs_acc_add(HsAcc& a, float gx, float gy, float r
   a.h12 += gy * rot;
 }
 
+// timing experiments only (build with `make TIMING=1`, run with HSGPU_DEBUG_TIMES): thread 0 of a matcher CTA accumulates
+// clock64() deltas per phase. Compiles to nothing in the product build.
+struct HsMatchTimer {
+#ifdef HS_MATCH_TIMING
+  long long t, acc[5];
+  unsigned long long* out;
+  __device__ __forceinline__ void begin(unsigned long long* o) { out = o; if (out && threadIdx.x == 0) { t = clock64(); for (int k = 0; k < 5; ++k) acc[k] = 0; } }
+  __device__ __forceinline__ void mark(int k) { if (out && threadIdx.x == 0) { long long c = clock64(); acc[k] += c - t; t = c; } }
+  __device__ __forceinline__ void end() { if (out && threadIdx.x == 0) for (int k = 0; k < 5; ++k) out[(size_t)blockIdx.x * 8 + k] = (unsigned long long)acc[k]; }
+#else
+  __device__ __forceinline__ void begin(unsigned long long*) {}
+  __device__ __forceinline__ void mark(int) {}
+  __device__ __forceinline__ void end() {}
+#endif
+};
+
 // One evaluation of getCompleteHessianDerivs by a whole CTA. The per-point work (transform, 4 gathers,
 // probabilities, the 9 products) is spread over all threads; the products go to shared memory as
 // prod[i][9] (stride 9 words: conflict-free for both the per-point writes and the per-sum reads).
@@ -213,7 +229,7 @@ __device__ __forceinline__ void hs_acc_add(HsAcc& a, float gx, float gy, float r
 //                   last-bit differences of H/dTr to >1e-4 m on some streams, so this is the mode that
 //                   meets the pose-parity bar.
 //   STRICT = false: every lane sums the points i = lane (mod 32) and a xor-butterfly combines them.
-// Must be called by all threads of the CTA; contains two __syncthreads. Only warp 0's return value is defined.
+// Must be called by all threads of the CTA; contains two __syncthreads. Only the serial warp's return value is defined.
 #define HS_NPROD 9
 
 __device__ __forceinline__ void hs_store_products(float* __restrict__ q, float gx, float gy, float rot, float fv) {
@@ -233,7 +249,7 @@ __device__ __forceinline__ void hs_store_products(float* __restrict__ q, float g
 template <bool STRICT, int PPT>
 __device__ __forceinline__ HsAcc hs_eval_cta(const float* __restrict__ val, const HsLevel& L, float ex, float ey, float sn, float cs,
                                              const float2* __restrict__ pts, const float2* preg, HsCellCache* cache, int n,
-                                             float pt_factor, float* __restrict__ prod) {
+                                             float pt_factor, float* __restrict__ prod, int serial_warp = 0, HsMatchTimer* mt = nullptr) {
   if (PPT > 0) {
 #pragma unroll
     for (int j = 0; j < (PPT > 0 ? PPT : 1); ++j) {
@@ -254,9 +270,10 @@ __device__ __forceinline__ HsAcc hs_eval_cta(const float* __restrict__ val, cons
     }
   }
   __syncthreads();
+  if (mt) mt->mark(2);
   HsAcc a = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  if (threadIdx.x < 32) {
-    const int lane = threadIdx.x;
+  if ((threadIdx.x >> 5) == serial_warp) {
+    const int lane = threadIdx.x & 31;
     float acc = 0.0f;
     if (STRICT) {
       if (lane < HS_NPROD) {
@@ -294,6 +311,7 @@ __device__ __forceinline__ HsAcc hs_eval_cta(const float* __restrict__ val, cons
       a.d0 = r[0]; a.d1 = r[1]; a.d2 = r[2]; a.h00 = r[3]; a.h11 = r[4]; a.h22 = r[5]; a.h01 = r[6]; a.h02 = r[7]; a.h12 = r[8];
     }
   }
+  if (mt) mt->mark(3);
   return a;
 }
 
@@ -332,6 +350,28 @@ __device__ __forceinline__ bool hs_gauss_newton_step(const HsAcc& a, float& ex, 
   return clamped;
 }
 
+// Tail of HectorSlamProcessor::update (HectorSlamProcessor.h:84-95), one thread per stream: store the matched pose, the
+// poseDifferenceLargerThan gate, and -- if the scan is to be integrated -- the update epoch the ray-caster works in.
+__device__ __forceinline__ void hs_match_tail(const HsParams& P, int slot, int s, float wx, float wy, float wth, bool mwm, int mode) {
+  P.last_pose[3 * s] = wx; P.last_pose[3 * s + 1] = wy; P.last_pose[3 * s + 2] = wth;
+  int integrate = 0;
+  if (mode == 0) {
+    float ux = P.last_update_pose[3 * s], uy = P.last_update_pose[3 * s + 1], uth = P.last_update_pose[3 * s + 2];
+    integrate = (hs_pose_difference_larger_than(wx, wy, wth, ux, uy, uth, P.min_dist, P.min_angle) || mwm) ? 1 : 0;
+    if (integrate) {
+      P.last_update_pose[3 * s] = wx; P.last_update_pose[3 * s + 1] = wy; P.last_update_pose[3 * s + 2] = wth;
+      int cur = P.cur_update_index[s];
+      P.slot_mark_base[slot] = cur;
+      P.cur_update_index[s] = cur + 3;        // OccGridMapBase.h:167
+      P.last_update_index[s] += 1;            // setUpdated() (OccGridMapBase.h:164)
+      P.slot_pose[3 * slot] = wx; P.slot_pose[3 * slot + 1] = wy; P.slot_pose[3 * slot + 2] = wth;
+      P.slot_sc[2 * slot] = hs_sinf(wth); P.slot_sc[2 * slot + 1] = hs_cosf(wth);   // Rotation2Df(pose[2]) of updateByScan (OccGridMapBase.h:130)
+      atomicAdd(&P.counters[1], 1ULL);
+    }
+  }
+  P.slot_integrate[slot] = integrate;
+}
+
 // k_match: HectorSlamProcessor::update minus the ray-cast (HSL/slam_main/HectorSlamProcessor.h:71-95):
 //   MapRepMultiMap::matchData (MapRepMultiMap.h:116-132) -> ScanMatcher::matchData per level, coarse to fine
 //   (ScanMatcher.h:54-190), then the poseDifferenceLargerThan gate and the per-stream bookkeeping.
@@ -352,6 +392,10 @@ __global__ void __launch_bounds__(HS_MATCH_THREADS) k_match(HsParams P, int n_sl
   const int slot = blockIdx.x;
   const int tid = threadIdx.x;
   if (slot >= n_slots) return;
+  // the serial part (sums, 3x3 solve, sin/cos) is carried by ONE warp; which one rotates with the CTA index, so that the
+  // serial warps of the CTAs sharing an SM sit on different SM sub-partitions (warp w issues from scheduler w mod 4)
+  const int sw = blockIdx.x & ((blockDim.x >> 5) - 1);
+  const bool serial = (tid >> 5) == sw, leader = tid == (sw << 5);
   const int s = hs_slot_stream(stream_ids, slot);
   int n = counts[slot];
   n = n < 0 ? 0 : (n > P.max_points ? P.max_points : n);
@@ -376,6 +420,8 @@ __global__ void __launch_bounds__(HS_MATCH_THREADS) k_match(HsParams P, int n_sl
       const float* val_s = P.val + (size_t)s * P.cells_per_stream;
       HsAcc a = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       unsigned clamps = 0;
+      HsMatchTimer mt;
+      mt.begin(P.dbg_times);
       float2 preg[PPT > 0 ? PPT : 1];
       HsCellCache cache[PPT > 0 ? PPT : 1];
       if (PPT > 0) {
@@ -391,54 +437,265 @@ __global__ void __launch_bounds__(HS_MATCH_THREADS) k_match(HsParams P, int n_sl
         float ex = 0.f, ey = 0.f, eth = wth;
 #pragma unroll
         for (int j = 0; j < (PPT > 0 ? PPT : 1); ++j) cache[j].key = -1;   // a new level is a new grid
-        if (tid < 32) {
+        if (serial) {
           hs_world_to_map(L, wx, wy, ex, ey);
-          if (tid == 0) { s_est[0] = ex; s_est[1] = ey; s_est[2] = eth; s_est[3] = hs_sinf(eth); s_est[4] = hs_cosf(eth); }
+          if (leader) { s_est[0] = ex; s_est[1] = ey; s_est[2] = eth; s_est[3] = hs_sinf(eth); s_est[4] = hs_cosf(eth); }
         }
         __syncthreads();
         for (int it = 0; it <= L.max_iter; ++it) {  // 1 + maxIterations evaluations, no early exit
           const float cex = s_est[0], cey = s_est[1], csn = s_est[3], ccs = s_est[4];
-          a = hs_eval_cta<STRICT, PPT>(val, L, cex, cey, csn, ccs, pts, preg, cache, n, L.pt_factor, hs_prod);
-          if (tid < 32) {
+          a = hs_eval_cta<STRICT, PPT>(val, L, cex, cey, csn, ccs, pts, preg, cache, n, L.pt_factor, hs_prod, sw, &mt);
+          if (serial) {
             clamps += hs_gauss_newton_step(a, ex, ey, eth) ? 1u : 0u;
-            if (tid == 0) { s_est[0] = ex; s_est[1] = ey; s_est[2] = eth; s_est[3] = hs_sinf(eth); s_est[4] = hs_cosf(eth); }
+            if (leader) { s_est[0] = ex; s_est[1] = ey; s_est[2] = eth; s_est[3] = hs_sinf(eth); s_est[4] = hs_cosf(eth); }
           }
           __syncthreads();
+          mt.mark(4);
         }
-        if (tid < 32) {
+        if (serial) {
           eth = hs_normalize_angle(eth);
           hs_map_to_world(L, ex, ey, wx, wy);
           wth = eth;
         }
       }
-      if (tid == 0) {
+      if (leader) {
         float* c = P.cov + 9 * (size_t)s;  // covMatrix = H of the last evaluation (ScanMatcher.h:184)
         c[0] = a.h00; c[1] = a.h01; c[2] = a.h02;
         c[3] = a.h01; c[4] = a.h11; c[5] = a.h12;
         c[6] = a.h02; c[7] = a.h12; c[8] = a.h22;
         if (clamps) atomicAdd(&P.counters[2], (unsigned long long)clamps);
       }
+      mt.end();
     }
   }
-  if (tid == 0) {
-    P.last_pose[3 * s] = wx; P.last_pose[3 * s + 1] = wy; P.last_pose[3 * s + 2] = wth;
-    int integrate = 0;
-    if (mode == 0) {
-      float ux = P.last_update_pose[3 * s], uy = P.last_update_pose[3 * s + 1], uth = P.last_update_pose[3 * s + 2];
-      integrate = (hs_pose_difference_larger_than(wx, wy, wth, ux, uy, uth, P.min_dist, P.min_angle) || mwm) ? 1 : 0;
-      if (integrate) {
-        P.last_update_pose[3 * s] = wx; P.last_update_pose[3 * s + 1] = wy; P.last_update_pose[3 * s + 2] = wth;
-        int cur = P.cur_update_index[s];
-        P.slot_mark_base[slot] = cur;
-        P.cur_update_index[s] = cur + 3;        // OccGridMapBase.h:167
-        P.last_update_index[s] += 1;            // setUpdated() (OccGridMapBase.h:164)
-        P.slot_pose[3 * slot] = wx; P.slot_pose[3 * slot + 1] = wy; P.slot_pose[3 * slot + 2] = wth;
-        P.slot_sc[2 * slot] = hs_sinf(wth); P.slot_sc[2 * slot + 1] = hs_cosf(wth);   // Rotation2Df(pose[2]) of updateByScan (OccGridMapBase.h:130)
-        atomicAdd(&P.counters[1], 1ULL);
+  if (leader) hs_match_tail(P, slot, s, wx, wy, wth, mwm, mode);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_match2: the same computation as k_match, organised so that the expensive part -- log-odds -> probability
+// (a double-precision expf and an IEEE division per cell) -- runs DENSE:
+//   step 1  every point: transform, bounds test, 2x2 block address k; the block's four probabilities are memoised in
+//           shared memory (pcache[i], key kcell[i]); points whose block changed since the last evaluation go to a miss list
+//           (Gauss-Newton steps on one level are mostly sub-cell, so after the first evaluation most points hit)
+//   step 2  the miss list x 4 cells is dealt out to ALL threads: gather (four loads in flight per thread), expf, division
+//   step 3  every point: bilinear value and gradient from pcache, the nine products -> prodT[9][pitch] (sum-major, so the
+//           strict sums read 4 consecutive products per 16-byte shared load)
+//   sums    as in hs_eval_cta: lanes 0..8 of warp 0, one dependent FADD chain per sum in the reference's point order.
+// Points, keys and probabilities live in shared memory, so any scan length works with one instantiation.
+// dynamic shared memory: 9 * pitch floats | max_points float4 | max_points float2 | max_points int | max_points ushort.
+__device__ __forceinline__ int hs_match2_pitch(int max_points) {   // >= max_points, == 4 (mod 32): conflict-free 16-byte row reads
+  return ((max_points + 27) & ~31) + 4;
+}
+
+template <bool STRICT>
+__device__ __forceinline__ HsAcc hs_eval_cta2(const float* __restrict__ val, const HsLevel& L, float ex, float ey, float sn, float cs,
+                                              const float2* __restrict__ spts, int n, float pt_factor, float* __restrict__ prodT, int pitch,
+                                              float4* __restrict__ pcache, int* __restrict__ kcell, unsigned short* __restrict__ miss,
+                                              int* __restrict__ s_nmiss, int serial_warp, HsMatchTimer& mt) {
+  const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31;
+  const int W = L.sx;
+  // step 1: block addresses, miss list
+  for (int i0 = 0; i0 < n; i0 += T) {
+    const int i = i0 + tid;
+    bool m = false;
+    if (i < n) {
+      const float2 p = spts[i];
+      const float px = p.x * pt_factor, py = p.y * pt_factor;
+      const float qx = (cs * px + (-sn) * py) + ex;  // Affine2f * v = linear*v + translation
+      const float qy = (sn * px + cs * py) + ey;
+      if (qx >= 0.0f && qx <= L.limx && qy >= 0.0f && qy <= L.limy) {  // !pointOutOfMapBounds
+        const int k = (int)qy * W + (int)qx;
+        if (k != kcell[i]) { kcell[i] = k; m = true; }
       }
     }
-    P.slot_integrate[slot] = integrate;
+    const unsigned b = __ballot_sync(0xffffffffu, m);
+    int base = 0;
+    if (lane == 0 && b) base = atomicAdd(s_nmiss, __popc(b));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (m) miss[base + __popc(b & ((1u << lane) - 1u))] = (unsigned short)i;
   }
+  __syncthreads();
+  mt.mark(0);
+  // step 2: probabilities of the missed blocks, one (block, corner) item per thread and turn
+  {
+    const int items = *s_nmiss << 2;
+    float* pc = reinterpret_cast<float*>(pcache);
+    for (int q0 = tid; q0 < items; q0 += 4 * T) {
+      float v[4];
+      int dst[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int q = q0 + u * T;
+        dst[u] = -1;
+        if (q < items) {
+          const int i = miss[q >> 2], c = q & 3;
+          dst[u] = (i << 2) | c;
+          v[u] = __ldg(val + kcell[i] + (c & 1) + ((c >> 1) ? W : 0));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (dst[u] >= 0) pc[dst[u]] = hs_probability(v[u]);
+    }
+  }
+  __syncthreads();
+  mt.mark(1);
+  // step 3: per-point terms and the nine products
+  for (int i = tid; i < n; i += T) {
+    const float2 p = spts[i];
+    const float px = p.x * pt_factor, py = p.y * pt_factor;
+    const float qx = (cs * px + (-sn) * py) + ex;
+    const float qy = (sn * px + cs * py) + ey;
+    float m = 0.0f, gx = 0.0f, gy = 0.0f;
+    if (qx >= 0.0f && qx <= L.limx && qy >= 0.0f && qy <= L.limy) {
+      const int ix = (int)qx, iy = (int)qy;
+      const float fx = qx - (float)ix, fy = qy - (float)iy;
+      const float4 c4 = pcache[i];
+      const float i0 = c4.x, i1 = c4.y, i2 = c4.z, i3 = c4.w;
+      const float dx1 = i0 - i1, dx2 = i2 - i3;
+      const float dy1 = i0 - i2, dy2 = i1 - i3;
+      const float x_inv = 1.0f - fx, y_inv = 1.0f - fy;
+      m = ((i0 * x_inv + i1 * fx) * y_inv) + ((i2 * x_inv + i3 * fx) * fy);
+      gx = -((dx1 * x_inv) + (dx2 * fx));  // the reference blends with the x factors here (OccGridMapUtil.h:344)
+      gy = -((dy1 * y_inv) + (dy2 * fy));  // ... and with the y factors here (:345)
+    }
+    const float fv = 1.0f - m;
+    const float rot = ((-sn * px - cs * py) * gx + (cs * px - sn * py) * gy);
+    float* q = prodT + i;
+    q[0] = gx * fv;             // dTr[0]
+    q[pitch] = gy * fv;         // dTr[1]
+    q[2 * pitch] = rot * fv;    // dTr[2]
+    q[3 * pitch] = gx * gx;     // H(0,0)
+    q[4 * pitch] = gy * gy;     // H(1,1)
+    q[5 * pitch] = rot * rot;   // H(2,2)
+    q[6 * pitch] = gx * gy;     // H(0,1)
+    q[7 * pitch] = gx * rot;    // H(0,2)
+    q[8 * pitch] = gy * rot;    // H(1,2)
+  }
+  __syncthreads();
+  mt.mark(2);
+  if (tid == 0) *s_nmiss = 0;   // every thread has read it (step 2) before the barrier above; next use is after the caller's barrier
+  HsAcc a = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if ((tid >> 5) == serial_warp) {
+    float r9[HS_NPROD];
+    if (STRICT) {
+      float acc = 0.0f;
+      if (lane < HS_NPROD) {
+        const float* q = prodT + lane * pitch;
+        const float4* q4 = reinterpret_cast<const float4*>(q);
+        const int n4 = n >> 2;
+        for (int i = 0; i < n4; ++i) {   // loads are independent of the chain and issue ahead of it
+          const float4 t = q4[i];
+          acc += t.x; acc += t.y; acc += t.z; acc += t.w;
+        }
+        for (int i = n4 << 2; i < n; ++i) acc += q[i];
+      }
+#pragma unroll
+      for (int k = 0; k < HS_NPROD; ++k) r9[k] = __shfl_sync(0xffffffffu, acc, k);
+    } else {
+#pragma unroll
+      for (int k = 0; k < HS_NPROD; ++k) r9[k] = 0.0f;
+      for (int i = lane; i < n; i += 32) {
+#pragma unroll
+        for (int k = 0; k < HS_NPROD; ++k) r9[k] += prodT[k * pitch + i];
+      }
+#pragma unroll
+      for (int m = 16; m >= 1; m >>= 1) {
+#pragma unroll
+        for (int k = 0; k < HS_NPROD; ++k) r9[k] += __shfl_xor_sync(0xffffffffu, r9[k], m);
+      }
+    }
+    a.d0 = r9[0]; a.d1 = r9[1]; a.d2 = r9[2]; a.h00 = r9[3]; a.h11 = r9[4]; a.h22 = r9[5]; a.h01 = r9[6]; a.h02 = r9[7]; a.h12 = r9[8];
+  }
+  mt.mark(3);
+  return a;
+}
+
+template <bool STRICT>
+__global__ void __launch_bounds__(HS_MATCH_THREADS) k_match2(HsParams P, int n_slots, const int32_t* __restrict__ stream_ids,
+                                                             const float2* __restrict__ points, const int32_t* __restrict__ counts,
+                                                             const float2* __restrict__ origos, const float* __restrict__ hints,
+                                                             const uint8_t* __restrict__ mwm_flags, int mode) {
+  extern __shared__ __align__(16) float hs_m2[];
+  __shared__ float s_est[5];  // ex, ey, eth, sin(eth), cos(eth)
+  __shared__ int s_nmiss;
+  const int pitch = hs_match2_pitch(P.max_points);
+  float* prodT = hs_m2;
+  float4* pcache = reinterpret_cast<float4*>(prodT + HS_NPROD * pitch);
+  float2* spts = reinterpret_cast<float2*>(pcache + P.max_points);
+  int* kcell = reinterpret_cast<int*>(spts + P.max_points);
+  unsigned short* miss = reinterpret_cast<unsigned short*>(kcell + P.max_points);
+  const int slot = blockIdx.x;
+  const int tid = threadIdx.x;
+  if (slot >= n_slots) return;
+  // the serial part (sums, 3x3 solve, sin/cos) is carried by ONE warp; which one rotates with the CTA index, so that the
+  // serial warps of the CTAs sharing an SM sit on different SM sub-partitions (warp w issues from scheduler w mod 4)
+  const int sw = blockIdx.x & ((blockDim.x >> 5) - 1);
+  const bool serial = (tid >> 5) == sw, leader = tid == (sw << 5);
+  const int s = hs_slot_stream(stream_ids, slot);
+  int n = counts[slot];
+  n = n < 0 ? 0 : (n > P.max_points ? P.max_points : n);
+  const float2* pts = points + (size_t)slot * P.max_points;
+  const bool mwm = mwm_flags ? (mwm_flags[slot] != 0) : false;
+  float wx, wy, wth;
+  if (hints) { wx = hints[3 * slot]; wy = hints[3 * slot + 1]; wth = hints[3 * slot + 2]; }
+  else { wx = P.last_pose[3 * s]; wy = P.last_pose[3 * s + 1]; wth = P.last_pose[3 * s + 2]; }
+
+  if (!mwm) {
+    // dataContainers[level-1].setFrom(dataContainer, 2^-level) (MapRepMultiMap.h:127): keep the level-0
+    // points of the last matched scan; the power-of-two factor is applied (exactly) where they are used.
+    float2* cp = reinterpret_cast<float2*>(P.coarse_pts) + (size_t)s * P.max_points;
+    for (int i = tid; i < n; i += blockDim.x) { const float2 p = pts[i]; cp[i] = p; spts[i] = p; }
+    if (tid == 0) {
+      P.coarse_cnt[s] = n;
+      float2 o = origos ? origos[slot] : make_float2(0.f, 0.f);
+      P.coarse_origo[2 * s] = o.x;
+      P.coarse_origo[2 * s + 1] = o.y;
+      s_nmiss = 0;
+    }
+    if (n != 0) {
+      const float* val_s = P.val + (size_t)s * P.cells_per_stream;
+      HsAcc a = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      unsigned clamps = 0;
+      HsMatchTimer mt;
+      mt.begin(P.dbg_times);
+      for (int level = P.n_levels - 1; level >= 0; --level) {
+        const HsLevel& L = P.lv[level];
+        const float* val = val_s + L.cell_offset;
+        float ex = 0.f, ey = 0.f, eth = wth;
+        for (int i = tid; i < n; i += blockDim.x) kcell[i] = -1;   // a new level is a new grid
+        if (serial) {
+          hs_world_to_map(L, wx, wy, ex, ey);
+          if (leader) { s_est[0] = ex; s_est[1] = ey; s_est[2] = eth; s_est[3] = hs_sinf(eth); s_est[4] = hs_cosf(eth); }
+        }
+        __syncthreads();
+        for (int it = 0; it <= L.max_iter; ++it) {  // 1 + maxIterations evaluations, no early exit
+          const float cex = s_est[0], cey = s_est[1], csn = s_est[3], ccs = s_est[4];
+          a = hs_eval_cta2<STRICT>(val, L, cex, cey, csn, ccs, spts, n, L.pt_factor, prodT, pitch, pcache, kcell, miss, &s_nmiss, sw, mt);
+          if (serial) {
+            clamps += hs_gauss_newton_step(a, ex, ey, eth) ? 1u : 0u;
+            if (leader) { s_est[0] = ex; s_est[1] = ey; s_est[2] = eth; s_est[3] = hs_sinf(eth); s_est[4] = hs_cosf(eth); }
+          }
+          __syncthreads();
+          mt.mark(4);
+        }
+        if (serial) {
+          eth = hs_normalize_angle(eth);
+          hs_map_to_world(L, ex, ey, wx, wy);
+          wth = eth;
+        }
+      }
+      if (leader) {
+        float* c = P.cov + 9 * (size_t)s;  // covMatrix = H of the last evaluation (ScanMatcher.h:184)
+        c[0] = a.h00; c[1] = a.h01; c[2] = a.h02;
+        c[3] = a.h01; c[4] = a.h11; c[5] = a.h12;
+        c[6] = a.h02; c[7] = a.h12; c[8] = a.h22;
+        if (clamps) atomicAdd(&P.counters[2], (unsigned long long)clamps);
+      }
+      mt.end();
+    }
+  }
+  if (leader) hs_match_tail(P, slot, s, wx, wy, wth, mwm, mode);
 }
 
 // k_force_integrate: teacher-forced integration set-up (hs_raycast_batch): refresh the coarse containers from
