@@ -151,6 +151,26 @@ int hs_match_batch(hs_engine* e, int n, const int32_t* stream_ids, const float* 
 int hs_raycast_batch(hs_engine* e, int n, const int32_t* stream_ids, const float* points, const int32_t* counts,
                      const float* origos, const float* poses_world);
 
+/* Off-path members of OccGridMapUtil (HSL/map/OccGridMapUtil.h:106-285; not called by update(), used for relocalisation
+ * scoring). Poses are MAP coordinates of the level, points already scaled to it; all host pointers.
+ * getResidualForState (:216-233) and getLikelihoodForState (:201-214) for n_poses hypotheses; either output may be NULL. */
+int hs_likelihood_batch(hs_engine* e, int stream, int level, const float* poses_map, int n_poses, const float* points,
+                        int n_points, float* residual_out, float* likelihood_out);
+/* getCovarianceForPose (:106-160): 7 sigma points (+-1.5 cells, +-0.05 rad) weighted by their likelihoods -> cov_map9;
+ * cov_world9 (may be NULL) = getCovMatrixWorldCoords (:162-189) of it. */
+int hs_covariance_for_pose(hs_engine* e, int stream, int level, const float* pose_map, const float* points, int n_points,
+                           float* cov_map9, float* cov_world9);
+/* interpMapValue (:241-285) -> values_out [n] and/or interpMapValueWithDerivatives (:287-347) -> derivs_out [n][3] at
+ * n map coordinates [n][2] of the level. */
+int hs_interp_map_value_batch(hs_engine* e, int stream, int level, const float* coords_map, int n, float* values_out, float* derivs_out);
+/* HectorMapTools::DistanceMeasurementProvider::checkOccupancyBresenhami
+ * (src/hector_slam/hector_map_tools/include/hector_map_tools/HectorMapTools.h:148-232) for n rays on the occupancy
+ * classification of a level (cell == 100 <=> log-odds > 0): begin/end cells [n][2] (x, y); dist_out [n] = distance to the
+ * first occupied cell in cells (truncated, as the reference) or -1; hit_cells_out [n][2] (may be NULL) = that cell or (-1,-1).
+ * getDist's world<->cell conversion (HectorMapTools.h:131-146) is the caller's (origin/resolution of the published map). */
+int hs_occupancy_ray_batch(hs_engine* e, int stream, int level, const int32_t* begin_cells, const int32_t* end_cells, int n,
+                           float* dist_out, int32_t* hit_cells_out);
+
 /* ---- map access --------------------------------------------------------------------------- */
 
 /* getGridMap(level) contents (HectorSlamProcessor.h:131): sx*sy cells, row-major cell[y*sx + x]. */
@@ -161,6 +181,22 @@ int hs_get_update_index(hs_engine* e, int stream, int level, int* update_index_o
 /* The occupancy classification HectorMappingRos::publishMap performs per cell (HectorMappingRos.cpp:447-470):
  * -1 unknown, 0 free, 100 occupied; sx*sy int8 values. */
 int hs_classify_level(hs_engine* e, int stream, int level, int8_t* occupancy_out);
+
+/* Everything of one stream that is not a grid cell (HectorSlamProcessor.h:141-153 members, the update counters of
+ * OccGridMapBase.h:265 / GridMapBase.h:399, and the coarse-level containers of MapRepMultiMap.h:151). Together with
+ * hs_download_level / hs_upload_level of every level this checkpoints and restores a stream bit for bit. */
+typedef struct {
+  float last_scan_match_pose[3];
+  float last_map_update_pose[3];
+  float last_scan_match_cov[9];
+  int32_t curr_update_index;
+  int32_t last_update_index;
+  int32_t coarse_count;
+  float coarse_origo[2];
+} hs_stream_state;
+/* coarse_points: [max_points][2] level-0 points behind MapRepMultiMap::dataContainers (may be NULL on export). */
+int hs_export_stream_state(hs_engine* e, int stream, hs_stream_state* out, float* coarse_points_out);
+int hs_import_stream_state(hs_engine* e, int stream, const hs_stream_state* in, const float* coarse_points);
 
 /* ---- bookkeeping -------------------------------------------------------------------------- */
 

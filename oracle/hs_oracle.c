@@ -224,6 +224,87 @@ static void interp_with_derivs(level_t* g, float cx, float cy, float* out3) {
   out3[2] = -((dy1 * y_inv) + (dy2 * fy));
 }
 
+/* OccGridMapUtil::interpMapValue (HSL/map/OccGridMapUtil.h:241-285): value only. */
+static float interp_map_value(level_t* g, float cx, float cy) {
+  if ((cx < 0.0f) || (cx > g->limit_x) || (cy < 0.0f) || (cy > g->limit_y)) return 0.0f;
+  int ix = (int)cx, iy = (int)cy;
+  float fx = cx - (float)ix, fy = cy - (float)iy;
+  int index = iy * g->sx + ix;
+  float i0 = cached_probability(g, index);
+  ++index;
+  float i1 = cached_probability(g, index);
+  index += g->sx - 1;
+  float i2 = cached_probability(g, index);
+  ++index;
+  float i3 = cached_probability(g, index);
+  float x_inv = 1.0f - fx, y_inv = 1.0f - fy;
+  return ((i0 * x_inv + i1 * fx) * y_inv) + ((i2 * x_inv + i3 * fx) * fy);
+}
+
+/* OccGridMapUtil::getResidualForState (HSL/map/OccGridMapUtil.h:216-233): sequential fp32 sum of 1 - interp. */
+static float residual_for_state(level_t* g, const float* pose, const float* pts, int n) {
+  float sin_rot = sinf(pose[2]);
+  float cos_rot = cosf(pose[2]);
+  float l[4] = { cos_rot, -sin_rot, sin_rot, cos_rot };
+  float t[2] = { pose[0], pose[1] };
+  float residual = 0.0f;
+  for (int i = 0; i < n; ++i) {
+    float qx, qy;
+    affine_apply(l, t, pts[2 * i], pts[2 * i + 1], &qx, &qy);
+    float funval = 1.0f - interp_map_value(g, qx, qy);
+    residual += funval;
+  }
+  return residual;
+}
+
+/* getLikelihoodForState / getLikelihoodForResidual (OccGridMapUtil.h:201-214): 1 - residual / n. */
+static float likelihood_for_state(level_t* g, const float* pose, const float* pts, int n) {
+  float resid = residual_for_state(g, pose, pts, n);
+  float sizef = (float)n;
+  return 1 - (resid / sizef);
+}
+
+/* OccGridMapUtil::getCovarianceForPose (OccGridMapUtil.h:106-160): 7 sigma points weighted by their likelihoods.
+ * Eigen semantics as restated in oracle/shim: likelihoods.sum() is the unrolled 7-term redux
+ * (a0 + (a1 + a2)) + ((a3 + a4) + (a5 + a6)); mean += sigma * lh elementwise;
+ * cov += (lh * inv) * (d * d^T) with the outer product formed first. cov row-major. */
+static void covariance_for_pose(level_t* g, const float* pose, const float* pts, int n, float* cov9) {
+  const float dtx = 1.5f, dty = 1.5f, dang = 0.05f;
+  float x = pose[0], y = pose[1], ang = pose[2];
+  float sp[7][3] = { { x + dtx, y, ang }, { x - dtx, y, ang }, { x, y + dty, ang }, { x, y - dty, ang },
+                     { x, y, ang + dang }, { x, y, ang - dang }, { x, y, ang } };
+  float lh[7];
+  for (int i = 0; i < 7; ++i) lh[i] = likelihood_for_state(g, sp[i], pts, n);
+  float sum = (lh[0] + (lh[1] + lh[2])) + ((lh[3] + lh[4]) + (lh[5] + lh[6]));
+  float inv = 1 / sum;
+  float mean[3] = { 0.0f, 0.0f, 0.0f };
+  for (int i = 0; i < 7; ++i)
+    for (int k = 0; k < 3; ++k) mean[k] += sp[i][k] * lh[i];
+  for (int k = 0; k < 3; ++k) mean[k] *= inv;
+  for (int k = 0; k < 9; ++k) cov9[k] = 0.0f;
+  for (int i = 0; i < 7; ++i) {
+    float d[3] = { sp[i][0] - mean[0], sp[i][1] - mean[1], sp[i][2] - mean[2] };
+    float w = lh[i] * inv;
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) cov9[3 * r + c] += w * (d[r] * d[c]);
+  }
+}
+
+/* OccGridMapUtil::getCovMatrixWorldCoords (OccGridMapUtil.h:162-189). Only the entries the reference assigns. */
+static void cov_matrix_world_coords(const level_t* g, const float* m, float* w) {
+  float scale = g->cell_length;
+  float scale_sq = scale * scale;
+  w[0] = m[0] * scale_sq;
+  w[4] = m[4] * scale_sq;
+  w[3] = m[3] * scale_sq;
+  w[1] = w[3];
+  w[6] = m[6] * scale;
+  w[2] = w[6];
+  w[7] = m[7] * scale;
+  w[5] = w[7];
+  w[8] = m[8];
+}
+
 /* OccGridMapUtil::getCompleteHessianDerivs (HSL/map/OccGridMapUtil.h:64-104). H row-major 3x3. */
 static void complete_hessian_derivs(level_t* g, const float* pose, const float* pts, int n, float* H, float* dTr) {
   float sin_rot = sinf(pose[2]);
@@ -484,6 +565,47 @@ void hso_update_by_scan_all(hso_proc* p, const float* pts, int n, float ox, floa
   multi_update_by_scan(p, pts, n, ox, oy, pose_world);
   on_map_updated(p);
 }
+float hso_interp_map_value(hso_proc* p, int level, float x, float y) { return interp_map_value(&p->lv[level], x, y); }
+float hso_residual_for_state(hso_proc* p, int level, const float* pose_map, const float* pts, int n) { return residual_for_state(&p->lv[level], pose_map, pts, n); }
+float hso_likelihood_for_state(hso_proc* p, int level, const float* pose_map, const float* pts, int n) { return likelihood_for_state(&p->lv[level], pose_map, pts, n); }
+void hso_covariance_for_pose(hso_proc* p, int level, const float* pose_map, const float* pts, int n, float* cov_map9, float* cov_world9) {
+  covariance_for_pose(&p->lv[level], pose_map, pts, n, cov_map9);
+  if (cov_world9) cov_matrix_world_coords(&p->lv[level], cov_map9, cov_world9);
+}
+
+/* HectorMapTools::DistanceMeasurementProvider::checkOccupancyBresenhami + bresenham2D
+ * (src/hector_slam/hector_map_tools/include/hector_map_tools/HectorMapTools.h:148-232) on an occupancy grid
+ * {-1, 0, 100}: first cell == 100 within min(5000, abs_da) steps from the begin cell (the end cell itself is not tested);
+ * returns (float)(int)|begin - hit| or -1. hit_xy is written only on a hit. */
+float hso_check_occupancy_bresenhami(const signed char* grid, int size_x, int size_y, int x0, int y0, int x1, int y1, int* hit_xy) {
+  if ((x0 < 0) || (x0 >= size_x) || (y0 < 0) || (y0 >= size_y)) return -1.0f;
+  if ((x1 < 0) || (x1 >= size_x) || (y1 < 0) || (y1 >= size_y)) return -1.0f;
+  int dx = x1 - x0, dy = y1 - y0;
+  unsigned int abs_dx = (unsigned int)abs(dx), abs_dy = (unsigned int)abs(dy);
+  int offset_dx = dx > 0 ? 1 : -1;
+  int offset_dy = (dy > 0 ? 1 : -1) * size_x;
+  unsigned int offset = (unsigned int)(y0 * size_x + x0);
+  unsigned int abs_da, abs_db;
+  int offset_a, offset_b;
+  if (abs_dx >= abs_dy) { abs_da = abs_dx; abs_db = abs_dy; offset_a = offset_dx; offset_b = offset_dy; }
+  else { abs_da = abs_dy; abs_db = abs_dx; offset_a = offset_dy; offset_b = offset_dx; }
+  int error_b = (int)(abs_da / 2);
+  unsigned int end = abs_da < 5000u ? abs_da : 5000u;
+  int end_offset = -1;
+  for (unsigned int i = 0; i < end; ++i) {
+    if (grid[offset] == 100) { end_offset = (int)offset; break; }
+    offset += (unsigned int)offset_a;
+    error_b += (int)abs_db;
+    if ((unsigned int)error_b >= abs_da) { offset += (unsigned int)offset_b; error_b -= (int)abs_da; }
+  }
+  if (end_offset == -1) return -1.0f;
+  int ex = end_offset % size_x, ey = end_offset / size_x;
+  float fx = (float)(x0 - ex), fy = (float)(y0 - ey);
+  int dist_map = (int)sqrtf(fx * fx + fy * fy);   /* ((begin - end).cast<float>()).norm() truncated to int */
+  if (hit_xy) { hit_xy[0] = ex; hit_xy[1] = ey; }
+  return (float)dist_map;
+}
+
 int hso_pose_difference_larger_than(const float* p1, const float* p2, float d, float a) { return pose_difference_larger_than(p1, p2, d, a); }
 float hso_normalize_angle(float a) { return normalize_angle(a); }
 unsigned long long hso_get_cell_visits(hso_proc* p) { return p->cell_visits; }

@@ -51,6 +51,14 @@ void hso_match_level(hso_proc* p, int level, const float* hint_world, const floa
 void hso_update_by_scan_level(hso_proc* p, int level, const float* pts, int n, float ox, float oy, const float* pose_world);
 void hso_refresh_coarse(hso_proc* p, const float* pts, int n, float ox, float oy);
 void hso_update_by_scan_all(hso_proc* p, const float* pts, int n, float ox, float oy, const float* pose_world);
+/* Off-path OccGridMapUtil members (HSL/map/OccGridMapUtil.h:106-285); poses in MAP coordinates of the level,
+ * pts already scaled to the level. */
+float hso_interp_map_value(hso_proc* p, int level, float x, float y);
+float hso_residual_for_state(hso_proc* p, int level, const float* pose_map, const float* pts, int n);
+float hso_likelihood_for_state(hso_proc* p, int level, const float* pose_map, const float* pts, int n);
+void hso_covariance_for_pose(hso_proc* p, int level, const float* pose_map, const float* pts, int n, float* cov_map9, float* cov_world9);
+/* HectorMapTools::DistanceMeasurementProvider::checkOccupancyBresenhami (hector_map_tools/HectorMapTools.h:148-232) */
+float hso_check_occupancy_bresenhami(const signed char* grid, int size_x, int size_y, int x0, int y0, int x1, int y1, int* hit_xy);
 int hso_pose_difference_larger_than(const float* p1, const float* p2, float d, float a);
 float hso_normalize_angle(float a);
 

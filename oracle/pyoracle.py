@@ -64,6 +64,11 @@ def _load(kind):
         "pose_difference_larger_than": (_I, [_P, _P, _F, _F]),
         "normalize_angle": (_F, [_F]),
         "run_streams": (ctypes.c_double, [_P, _I, _I, _I, _P, _P, _I, _I, _P, _P]),
+        "interp_map_value": (_F, [_P, _I, _F, _F]),
+        "residual_for_state": (_F, [_P, _I, _P, _P, _I]),
+        "likelihood_for_state": (_F, [_P, _I, _P, _P, _I]),
+        "covariance_for_pose": (None, [_P, _I, _P, _P, _I, _P, _P]),
+        "check_occupancy_bresenhami": (_F, [_P, _I, _I, _I, _I, _I, _I, _P]),
     }
     if kind == "port":
         sig["get_cell_visits"] = (ctypes.c_ulonglong, [_P])
@@ -193,8 +198,36 @@ class CpuProcessor:
         self.f["refresh_coarse"](self.h, points.ctypes.data, n, float(origo[0]), float(origo[1]))
         self.f["update_by_scan_all"](self.h, points.ctypes.data, n, float(origo[0]), float(origo[1]), pose_world.ctypes.data)
 
+    # off-path OccGridMapUtil members (OccGridMapUtil.h:106-285); poses in MAP coordinates, points scaled to the level
+    def interp_map_value(self, level, x, y): return float(self.f["interp_map_value"](self.h, level, float(x), float(y)))
+
+    def residual_for_state(self, level, pose_map, points):
+        points = _f32(points).reshape(-1, 2); pose_map = _f32(pose_map)
+        return float(self.f["residual_for_state"](self.h, level, pose_map.ctypes.data, points.ctypes.data, points.shape[0]))
+
+    def likelihood_for_state(self, level, pose_map, points):
+        points = _f32(points).reshape(-1, 2); pose_map = _f32(pose_map)
+        return float(self.f["likelihood_for_state"](self.h, level, pose_map.ctypes.data, points.ctypes.data, points.shape[0]))
+
+    def covariance_for_pose(self, level, pose_map, points):
+        """(covMatrixMap, getCovMatrixWorldCoords(covMatrixMap)); entries the reference leaves unset in the latter are 0 here."""
+        points = _f32(points).reshape(-1, 2); pose_map = _f32(pose_map)
+        cm = np.zeros(9, np.float32); cw = np.zeros(9, np.float32)
+        self.f["covariance_for_pose"](self.h, level, pose_map.ctypes.data, points.ctypes.data, points.shape[0], cm.ctypes.data, cw.ctypes.data)
+        return cm.reshape(3, 3), cw.reshape(3, 3)
+
     def cell_visits(self): return int(self.f["get_cell_visits"](self.h))
     def integrations(self): return int(self.f["get_integrations"](self.h))
+
+
+def check_occupancy_bresenhami(kind, grid, begin, end):
+    """HectorMapTools::DistanceMeasurementProvider::checkOccupancyBresenhami on an int8 occupancy grid [sy][sx]:
+    (distance in cells or -1, hit cell or None)."""
+    grid = np.ascontiguousarray(grid, np.int8)
+    hit = np.full(2, -1, np.int32)
+    d = _load(kind)["check_occupancy_bresenhami"](grid.ctypes.data, grid.shape[1], grid.shape[0], int(begin[0]), int(begin[1]),
+                                                  int(end[0]), int(end[1]), hit.ctypes.data)
+    return float(d), (hit.copy() if d >= 0 else None)
 
 
 def pose_difference_larger_than(kind, p1, p2, d, a):

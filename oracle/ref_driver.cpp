@@ -8,7 +8,9 @@
 //   * to generate the golden fixtures under tests/golden/ (tests/golden/make_golden.py),
 //   * optionally as the CPU baseline ("kind": "reference") in bench.py.
 // Reference entry points exercised: HectorSlamProcessor (slam_main/HectorSlamProcessor.h:50-154),
-// OccGridMapUtil::getCompleteHessianDerivs (map/OccGridMapUtil.h:64-104),
+// OccGridMapUtil::getCompleteHessianDerivs (map/OccGridMapUtil.h:64-104) and its off-path members
+// (getResidualForState, getLikelihoodForState, getCovarianceForPose, interpMapValue: :106-285),
+// HectorMapTools::DistanceMeasurementProvider (hector_map_tools/HectorMapTools.h:118-236),
 // OccGridMapBase::updateByScan (map/OccGridMapBase.h:121-168),
 // util::poseDifferenceLargerThan (util/UtilFunctions.h:73-92).
 
@@ -28,6 +30,7 @@
 #include <tf/LinearMath/Transform.h>
 
 #include "slam_main/HectorSlamProcessor.h"
+#include "hector_map_tools/HectorMapTools.h"   // DistanceMeasurementProvider (occupancy ray queries)
 
 namespace {
 
@@ -183,6 +186,48 @@ void hsref_update_by_scan_all(void* h, const float* pts, int n, float ox, float 
   p->multi().updateByScan(p->scratch, Eigen::Vector3f(pose_world[0], pose_world[1], pose_world[2]));
   p->multi().onMapUpdated();
 }
+// Off-path OccGridMapUtil members (map/OccGridMapUtil.h:106-285); pose in MAP coordinates, pts scaled to the level.
+float hsref_interp_map_value(void* h, int level, float x, float y) {
+  return static_cast<Proc*>(h)->level(level).gridMapUtil->interpMapValue(Eigen::Vector2f(x, y));
+}
+float hsref_residual_for_state(void* h, int level, const float* pose_map, const float* pts, int n) {
+  Proc* p = static_cast<Proc*>(h);
+  fill(p->scratch, pts, n, 0.f, 0.f);
+  return p->level(level).gridMapUtil->getResidualForState(Eigen::Vector3f(pose_map[0], pose_map[1], pose_map[2]), p->scratch);
+}
+float hsref_likelihood_for_state(void* h, int level, const float* pose_map, const float* pts, int n) {
+  Proc* p = static_cast<Proc*>(h);
+  fill(p->scratch, pts, n, 0.f, 0.f);
+  return p->level(level).gridMapUtil->getLikelihoodForState(Eigen::Vector3f(pose_map[0], pose_map[1], pose_map[2]), p->scratch);
+}
+void hsref_covariance_for_pose(void* h, int level, const float* pose_map, const float* pts, int n, float* cov_map9, float* cov_world9) {
+  Proc* p = static_cast<Proc*>(h);
+  fill(p->scratch, pts, n, 0.f, 0.f);
+  Util* util = p->level(level).gridMapUtil;
+  Eigen::Matrix3f c = util->getCovarianceForPose(Eigen::Vector3f(pose_map[0], pose_map[1], pose_map[2]), p->scratch);
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) cov_map9[3 * i + j] = c(i, j);
+  if (cov_world9) {
+    Eigen::Matrix3f w = util->getCovMatrixWorldCoords(c);
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) cov_world9[3 * i + j] = w(i, j);
+  }
+}
+
+// HectorMapTools::DistanceMeasurementProvider::checkOccupancyBresenhami on a caller-supplied occupancy grid.
+float hsref_check_occupancy_bresenhami(const signed char* grid, int size_x, int size_y, int x0, int y0, int x1, int y1, int* hit_xy) {
+  std::shared_ptr<nav_msgs::OccupancyGrid> map(new nav_msgs::OccupancyGrid());
+  map->info.resolution = 1.0f;
+  map->info.width = (uint32_t)size_x;
+  map->info.height = (uint32_t)size_y;
+  map->info.origin.position.x = 0.0; map->info.origin.position.y = 0.0; map->info.origin.position.z = 0.0;
+  map->data.assign(grid, grid + (size_t)size_x * size_y);
+  HectorMapTools::DistanceMeasurementProvider dmp;
+  dmp.setMap(map);
+  Eigen::Vector2i hit(-1, -1);
+  float d = dmp.checkOccupancyBresenhami(Eigen::Vector2i(x0, y0), Eigen::Vector2i(x1, y1), &hit);
+  if (hit_xy && d >= 0.0f) { hit_xy[0] = hit[0]; hit_xy[1] = hit[1]; }
+  return d;
+}
+
 int hsref_pose_difference_larger_than(const float* p1, const float* p2, float d, float a) {
   return util::poseDifferenceLargerThan(Eigen::Vector3f(p1[0], p1[1], p1[2]), Eigen::Vector3f(p2[0], p2[1], p2[2]), d, a) ? 1 : 0;
 }

@@ -83,6 +83,28 @@ def main():
             arrays["%s/kat_l%d_poses" % (name, level)] = hyp
             arrays["%s/kat_l%d_H" % (name, level)] = H
             arrays["%s/kat_l%d_dTr" % (name, level)] = d
+            # off-path OccGridMapUtil members (OccGridMapUtil.h:106-285) on the same hypotheses
+            arrays["%s/kat_l%d_resid" % (name, level)] = np.array([p.residual_for_state(level, h, scaled) for h in hyp], np.float32)
+            arrays["%s/kat_l%d_lh" % (name, level)] = np.array([p.likelihood_for_state(level, h, scaled) for h in hyp], np.float32)
+            cc = [p.covariance_for_pose(level, h, scaled) for h in hyp[:3]]
+            arrays["%s/kat_l%d_covmap" % (name, level)] = np.stack([c[0] for c in cc])
+            arrays["%s/kat_l%d_covworld" % (name, level)] = np.stack([c[1] for c in cc])
+            coords = (hyp[:, :2] + rng.uniform(-40, 40, (12, 2)) / (1 << level)).astype(np.float32)
+            arrays["%s/kat_l%d_coords" % (name, level)] = coords
+            arrays["%s/kat_l%d_interp" % (name, level)] = np.array([p.interp_map_value(level, c[0], c[1]) for c in coords], np.float32)
+        # hector_map_tools occupancy ray queries on the published (classified) level-0 map
+        size = c["cfg"]["size"]
+        v0 = p.download_level(0)["logOddsVal"].reshape(size, size)
+        occ = np.where(v0 < 0, 0, np.where(v0 > 0, 100, -1)).astype(np.int8)
+        b0 = p.world_to_map(0, poses[-1])[:2].astype(np.int32)
+        ends = (b0[None, :] + rng.integers(-size // 3, size // 3, (24, 2))).astype(np.int32)
+        ends[0] = b0                      # begin == end
+        ends[1] = (size + 5, b0[1])       # end outside the map
+        rays = [pyoracle.check_occupancy_bresenhami("ref", occ, b0, e) for e in ends]
+        arrays[name + "/ray_begin"] = b0
+        arrays[name + "/ray_ends"] = ends
+        arrays[name + "/ray_dist"] = np.array([r[0] for r in rays], np.float32)
+        arrays[name + "/ray_hit"] = np.array([r[1] if r[1] is not None else (-1, -1) for r in rays], np.int32)
         nz = [int((p.download_level(l)["logOddsVal"] != 0).sum()) for l in range(c["cfg"]["levels"])]
         meta["cases"][name] = {"cfg": c["cfg"], "params": c["params"], "mwm_every": c["mwm_every"], "n_scans": c["n_scans"],
                                "level_digests_sha256": digests, "nonzero_cells": nz}

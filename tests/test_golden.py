@@ -57,6 +57,25 @@ def test_stream_golden(oracle, have_ref, kind, case):
         H, d = p.hessian_derivs_batch(l, z["%s/kat_l%d_poses" % (case, l)], scaled)
         assert np.array_equal(bits(H), bits(z["%s/kat_l%d_H" % (case, l)]))
         assert np.array_equal(bits(d), bits(z["%s/kat_l%d_dTr" % (case, l)]))
+        # off-path members: getResidualForState / getLikelihoodForState / getCovarianceForPose / interpMapValue
+        hyp = z["%s/kat_l%d_poses" % (case, l)]
+        r = np.array([p.residual_for_state(l, h, scaled) for h in hyp], np.float32)
+        lh = np.array([p.likelihood_for_state(l, h, scaled) for h in hyp], np.float32)
+        assert np.array_equal(bits(r), bits(z["%s/kat_l%d_resid" % (case, l)])) and np.array_equal(bits(lh), bits(z["%s/kat_l%d_lh" % (case, l)]))
+        for i in range(3):
+            cm, cw = p.covariance_for_pose(l, hyp[i], scaled)
+            assert np.array_equal(bits(cm), bits(z["%s/kat_l%d_covmap" % (case, l)][i]))
+            assert np.array_equal(bits(cw), bits(z["%s/kat_l%d_covworld" % (case, l)][i]))
+        iv = np.array([p.interp_map_value(l, c[0], c[1]) for c in z["%s/kat_l%d_coords" % (case, l)]], np.float32)
+        assert np.array_equal(bits(iv), bits(z["%s/kat_l%d_interp" % (case, l)]))
+    # occupancy ray queries (hector_map_tools) on the classified level-0 map
+    size = m["cfg"]["size"]
+    v0 = p.download_level(0)["logOddsVal"].reshape(size, size)
+    occ = np.where(v0 < 0, 0, np.where(v0 > 0, 100, -1)).astype(np.int8)
+    for e, d_ref, h_ref in zip(z[case + "/ray_ends"], z[case + "/ray_dist"], z[case + "/ray_hit"]):
+        d_got, h_got = oracle.check_occupancy_bresenhami(kind, occ, z[case + "/ray_begin"], e)
+        assert d_got == d_ref and (h_got is None or np.array_equal(h_got, h_ref))
+    assert (z[case + "/ray_dist"] >= 0).sum() >= 3, "golden rays should hit something"
     p.close()
 
 
@@ -87,3 +106,18 @@ def test_stream_golden_gpu(hs, case):
             H, d = eng.hessian_derivs_batch(0, l, z["%s/kat_l%d_poses" % (case, l)], scaled)
             assert np.array_equal(bits(H), bits(z["%s/kat_l%d_H" % (case, l)]))
             assert np.array_equal(bits(d), bits(z["%s/kat_l%d_dTr" % (case, l)]))
+            # off-path OccGridMapUtil members and the hector_map_tools ray query, against the reference's golden outputs
+            hyp = z["%s/kat_l%d_poses" % (case, l)]
+            r, lh = eng.likelihood_batch(0, l, hyp, scaled)
+            assert np.array_equal(bits(r), bits(z["%s/kat_l%d_resid" % (case, l)])) and np.array_equal(bits(lh), bits(z["%s/kat_l%d_lh" % (case, l)]))
+            for i in range(3):
+                cm, cw = eng.covariance_for_pose(0, l, hyp[i], scaled)
+                assert np.array_equal(bits(cm), bits(z["%s/kat_l%d_covmap" % (case, l)][i]))
+                assert np.array_equal(bits(cw), bits(z["%s/kat_l%d_covworld" % (case, l)][i]))
+            coords = z["%s/kat_l%d_coords" % (case, l)]
+            iv, dv = eng.interp_map_value_batch(0, l, coords)
+            assert np.array_equal(bits(iv), bits(z["%s/kat_l%d_interp" % (case, l)]))
+            assert np.array_equal(bits(dv[:, 0]), bits(iv))   # interpMapValueWithDerivatives' value equals interpMapValue
+        ends = z[case + "/ray_ends"]
+        dist, hit = eng.occupancy_ray_batch(0, 0, np.repeat(z[case + "/ray_begin"][None, :], len(ends), 0), ends)
+        assert np.array_equal(dist, z[case + "/ray_dist"]) and np.array_equal(hit, z[case + "/ray_hit"])

@@ -216,3 +216,78 @@ def test_match_only_and_pose_hypotheses(hs, oracle):
     Hc, dc = p.hessian_derivs_batch(0, hyp, scan)
     assert np.array_equal(bits(H), bits(Hc)) and np.array_equal(bits(d), bits(dc))
     eng.close()
+
+
+def test_checkpoint_restore_continues_bit_exact(hs, oracle):
+    """hs_export_stream_state + hs_download_level of every level is a complete checkpoint: restored into another slot of
+    another engine (after a reset elsewhere moved the counters), the stream continues bit for bit like the original --
+    including the update markers, whose counter is not reset by reset() -- and like the CPU oracle."""
+    n_scans, cut = 24, 11
+    sc, ranges, pts, cnt, truth = make_streams(hs, 1, n_scans, seed0=4711)
+    eng, procs = setup_pair(hs, oracle, 1, dist=0.2, ang=0.3)
+    for k in range(cut):
+        if k == 5:
+            eng.reset(); procs[0].reset()        # counters keep counting across reset()
+        out, _ = eng.update_batch(pts[k], cnt[k])
+        procs[0].update(pts[k, 0], cnt[k, 0], hint=procs[0].pose())
+    state, coarse = eng.export_stream_state(0)
+    levels = [eng.download_level(0, l) for l in range(3)]
+    with hs.Engine(n_streams=3, max_points=360) as other:
+        other.set_update_factor_free(0.4); other.set_update_factor_occupied(0.9)
+        other.set_map_update_min_dist_diff(0.2); other.set_map_update_min_angle_diff(0.3)
+        other.import_stream_state(2, state, coarse)
+        for l in range(3):
+            other.upload_level(2, l, levels[l])
+        for k in range(cut, n_scans):
+            a, ca = eng.update_batch(pts[k], cnt[k])
+            b, cb = other.update_batch(pts[k], cnt[k], stream_ids=[2])
+            ref = procs[0].update(pts[k, 0], cnt[k, 0], hint=procs[0].pose())
+            assert np.array_equal(bits(a[0]), bits(b[0])) and np.array_equal(bits(a[0]), bits(ref)) and np.array_equal(bits(ca), bits(cb)), k
+        assert_same_maps(other, procs, 3, streams=[2])
+        assert other.update_index(2, 0) == eng.update_index(0, 0) == procs[0].update_index(0)
+    eng.close()
+    for p in procs:
+        p.close()
+
+
+def test_offpath_members_on_random_maps(hs, oracle):
+    """getResidualForState / getLikelihoodForState / getCovarianceForPose / interpMapValue(+WithDerivatives) and the
+    occupancy ray query on random maps, incl. hypotheses and coordinates outside the map limits, empty point sets aside."""
+    rng = np.random.default_rng(21)
+    size = 256
+    with hs.Engine(0.05, size, size, (0.5, 0.5), 2, n_streams=2, max_points=512) as eng:
+        p = oracle.CpuProcessor("port", 0.05, size, size, (0.5, 0.5), 2)
+        for l in range(2):
+            n = (size >> l) ** 2
+            cells = np.zeros(n, hs.CELL_DTYPE)
+            cells["logOddsVal"] = rng.normal(0, 2, n).astype(np.float32)
+            cells["logOddsVal"][rng.random(n) < 0.5] = 0.0
+            cells["updateIndex"] = -1
+            eng.upload_level(1, l, cells); p.upload_level(l, cells)
+            lim = size >> l
+            pts = rng.uniform(-0.3 * lim, 0.3 * lim, (417, 2)).astype(np.float32)
+            poses = np.concatenate([rng.uniform(-0.1 * lim, 1.1 * lim, (64, 2)), rng.uniform(-4, 4, (64, 1))], 1).astype(np.float32)
+            r, lh = eng.likelihood_batch(1, l, poses, pts)
+            r_ref = np.array([p.residual_for_state(l, q, pts) for q in poses], np.float32)
+            lh_ref = np.array([p.likelihood_for_state(l, q, pts) for q in poses], np.float32)
+            assert np.array_equal(bits(r), bits(r_ref)) and np.array_equal(bits(lh), bits(lh_ref))
+            for q in poses[:4]:
+                cm, cw = eng.covariance_for_pose(1, l, q, pts)
+                cm_ref, cw_ref = p.covariance_for_pose(l, q, pts)
+                assert np.array_equal(bits(cm), bits(cm_ref)) and np.array_equal(bits(cw), bits(cw_ref))
+            coords = rng.uniform(-3, lim + 3, (300, 2)).astype(np.float32)
+            coords[:4] = [(0, 0), (lim - 2, lim - 2), (lim - 1.999, 5), (5, -0.0001)]
+            iv, dv = eng.interp_map_value_batch(1, l, coords)
+            iv_ref = np.array([p.interp_map_value(l, c[0], c[1]) for c in coords], np.float32)
+            dv_ref = np.stack([p.interp_with_derivs(l, c[0], c[1]) for c in coords])
+            assert np.array_equal(bits(iv), bits(iv_ref)) and np.array_equal(bits(dv), bits(dv_ref))
+            v = cells["logOddsVal"].reshape(lim, lim)
+            occ = np.where(v < 0, 0, np.where(v > 0, 100, -1)).astype(np.int8)
+            occ_sparse = occ.copy()
+            begins = rng.integers(-2, lim + 2, (200, 2)).astype(np.int32)
+            ends = rng.integers(-2, lim + 2, (200, 2)).astype(np.int32)
+            dist, hit = eng.occupancy_ray_batch(1, l, begins, ends)
+            for i in range(200):
+                d_ref, h_ref = oracle.check_occupancy_bresenhami("port", occ_sparse, begins[i], ends[i])
+                assert dist[i] == d_ref and np.array_equal(hit[i], h_ref if h_ref is not None else (-1, -1)), i
+        p.close()

@@ -48,6 +48,12 @@ class HsStats(ctypes.Structure):
                 ("cell_visits", ctypes.c_uint64)]
 
 
+class HsStreamState(ctypes.Structure):
+    _fields_ = [("last_scan_match_pose", ctypes.c_float * 3), ("last_map_update_pose", ctypes.c_float * 3),
+                ("last_scan_match_cov", ctypes.c_float * 9), ("curr_update_index", ctypes.c_int32),
+                ("last_update_index", ctypes.c_int32), ("coarse_count", ctypes.c_int32), ("coarse_origo", ctypes.c_float * 2)]
+
+
 class HsKernelTimes(ctypes.Structure):
     _fields_ = [("ms", ctypes.c_double * 3), ("launches", ctypes.c_uint64 * 3)]
 
@@ -112,6 +118,11 @@ def lib():
         "hs_download_level": (_I, [_P, _I, _I, _P]), "hs_upload_level": (_I, [_P, _I, _I, _P]),
         "hs_get_update_index": (_I, [_P, _I, _I, _P]), "hs_classify_level": (_I, [_P, _I, _I, _P]),
         "hs_get_stats": (_I, [_P, _P]),
+        "hs_likelihood_batch": (_I, [_P, _I, _I, _P, _I, _P, _I, _P, _P]),
+        "hs_covariance_for_pose": (_I, [_P, _I, _I, _P, _P, _I, _P, _P]),
+        "hs_interp_map_value_batch": (_I, [_P, _I, _I, _P, _I, _P, _P]),
+        "hs_occupancy_ray_batch": (_I, [_P, _I, _I, _P, _P, _I, _P, _P]),
+        "hs_export_stream_state": (_I, [_P, _I, _P, _P]), "hs_import_stream_state": (_I, [_P, _I, _P, _P]),
         "hs_profile_enable": (_I, [_P, _I]), "hs_profile_collect": (_I, [_P, _P]),
         "hs_scene_preset": (_I, [_I, _P]),
         "hs_scangen_batch": (_I, [_P, ctypes.c_uint64, _I, _I, _I, _P, _P, _I]),
@@ -308,6 +319,58 @@ class Engine:
         _check(lib().hs_hessian_derivs_batch(self._h, stream, level, poses_map.ctypes.data, n, points.ctypes.data,
                                              points.shape[0], H.ctypes.data, d.ctypes.data), "hs_hessian_derivs_batch")
         return H.reshape(n, 3, 3), d
+
+    # off-path OccGridMapUtil members (OccGridMapUtil.h:106-285) and hector_map_tools ray queries
+    def likelihood_batch(self, stream, level, poses_map, points):
+        """(getResidualForState, getLikelihoodForState) per pose hypothesis."""
+        poses_map = _arr(poses_map, np.float32).reshape(-1, 3)
+        points = _arr(points, np.float32).reshape(-1, 2)
+        n = poses_map.shape[0]
+        r = np.empty(n, np.float32)
+        lh = np.empty(n, np.float32)
+        _check(lib().hs_likelihood_batch(self._h, stream, level, poses_map.ctypes.data, n, points.ctypes.data, points.shape[0],
+                                         r.ctypes.data, lh.ctypes.data), "hs_likelihood_batch")
+        return r, lh
+
+    def covariance_for_pose(self, stream, level, pose_map, points):
+        pose_map = _arr(pose_map, np.float32).reshape(3)
+        points = _arr(points, np.float32).reshape(-1, 2)
+        cm = np.empty(9, np.float32)
+        cw = np.empty(9, np.float32)
+        _check(lib().hs_covariance_for_pose(self._h, stream, level, pose_map.ctypes.data, points.ctypes.data, points.shape[0],
+                                            cm.ctypes.data, cw.ctypes.data), "hs_covariance_for_pose")
+        return cm.reshape(3, 3), cw.reshape(3, 3)
+
+    def interp_map_value_batch(self, stream, level, coords_map):
+        """(interpMapValue [n], interpMapValueWithDerivatives [n][3])."""
+        coords_map = _arr(coords_map, np.float32).reshape(-1, 2)
+        n = coords_map.shape[0]
+        v = np.empty(n, np.float32)
+        d = np.empty((n, 3), np.float32)
+        _check(lib().hs_interp_map_value_batch(self._h, stream, level, coords_map.ctypes.data, n, v.ctypes.data, d.ctypes.data),
+               "hs_interp_map_value_batch")
+        return v, d
+
+    def occupancy_ray_batch(self, stream, level, begin_cells, end_cells):
+        """checkOccupancyBresenhami per ray: (distance in cells or -1 [n], hit cell or (-1,-1) [n][2])."""
+        b = _arr(begin_cells, np.int32).reshape(-1, 2)
+        en = _arr(end_cells, np.int32).reshape(-1, 2)
+        n = b.shape[0]
+        dist = np.empty(n, np.float32)
+        hit = np.empty((n, 2), np.int32)
+        _check(lib().hs_occupancy_ray_batch(self._h, stream, level, b.ctypes.data, en.ctypes.data, n, dist.ctypes.data, hit.ctypes.data),
+               "hs_occupancy_ray_batch")
+        return dist, hit
+
+    def export_stream_state(self, stream):
+        st = HsStreamState()
+        pts = np.zeros((self.max_points, 2), np.float32)
+        _check(lib().hs_export_stream_state(self._h, stream, ctypes.byref(st), pts.ctypes.data), "hs_export_stream_state")
+        return st, pts
+
+    def import_stream_state(self, stream, state, coarse_points):
+        coarse_points = _arr(coarse_points, np.float32, (self.max_points, 2))
+        _check(lib().hs_import_stream_state(self._h, stream, ctypes.byref(state), coarse_points.ctypes.data), "hs_import_stream_state")
 
     # state access
     def poses(self, first=0, n=None):

@@ -702,6 +702,186 @@ int hs_raycast_batch(hs_engine* e, int n, const int32_t* stream_ids, const float
   return HS_OK;
 }
 
+// ---- off-path OccGridMapUtil members, occupancy ray queries, stream state ------------------------
+
+static int check_stream_level(const hs_engine* e, int stream, int level) {
+  if (!e || stream < 0 || stream >= e->P.n_streams || level < 0 || level >= e->P.n_levels) return HS_ERR_INVALID_ARG;
+  return HS_OK;
+}
+
+int hs_likelihood_batch(hs_engine* e, int stream, int level, const float* poses_map, int n_poses, const float* points,
+                        int n_points, float* residual_out, float* likelihood_out) {
+  int st = check_stream_level(e, stream, level);
+  if (st != HS_OK) return st;
+  if (n_poses < 0 || n_points < 0) return HS_ERR_INVALID_ARG;
+  if (n_poses == 0) return HS_OK;
+  if (!poses_map || (!points && n_points > 0)) return HS_ERR_INVALID_ARG;
+  HS_CK(cudaSetDevice(e->device));
+  auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t b_poses = (size_t)n_poses * 3 * sizeof(float), b_pts = (size_t)(n_points > 0 ? n_points : 1) * 2 * sizeof(float);
+  const size_t b_out = (size_t)n_poses * sizeof(float);
+  const size_t o_pts = align(b_poses), o_r = o_pts + align(b_pts), o_l = o_r + align(b_out), total = o_l + align(b_out);
+  if ((st = ensure_scratch(e, total)) != HS_OK) return st;
+  char* base = (char*)e->d_scratch;
+  HS_CK(cudaMemcpyAsync(base, poses_map, b_poses, cudaMemcpyHostToDevice, e->stream));
+  if (n_points > 0) HS_CK(cudaMemcpyAsync(base + o_pts, points, (size_t)n_points * 2 * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  e->h2d_bytes += b_poses + (size_t)n_points * 8;
+  const size_t smem = (size_t)(n_points > 0 ? n_points : 1) * sizeof(float);
+  if (smem > 200 * 1024) return HS_ERR_INVALID_ARG;
+  if (smem > 48 * 1024) {
+    HS_CK(cudaFuncSetAttribute(k_residual<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HS_CK(cudaFuncSetAttribute(k_residual<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  if (e->P.strict)
+    k_residual<true><<<n_poses, HS_MATCH_THREADS, smem, e->stream>>>(e->P, stream, level, (const float*)base, n_poses, (const float2*)(base + o_pts),
+                                                                    n_points, (float*)(base + o_r), (float*)(base + o_l));
+  else
+    k_residual<false><<<n_poses, HS_MATCH_THREADS, smem, e->stream>>>(e->P, stream, level, (const float*)base, n_poses, (const float2*)(base + o_pts),
+                                                                     n_points, (float*)(base + o_r), (float*)(base + o_l));
+  HS_LAUNCHED(e);
+  if (residual_out) { HS_CK(cudaMemcpyAsync(residual_out, base + o_r, b_out, cudaMemcpyDeviceToHost, e->stream)); e->d2h_bytes += b_out; }
+  if (likelihood_out) { HS_CK(cudaMemcpyAsync(likelihood_out, base + o_l, b_out, cudaMemcpyDeviceToHost, e->stream)); e->d2h_bytes += b_out; }
+  HS_CK(cudaStreamSynchronize(e->stream));
+  return HS_OK;
+}
+
+// OccGridMapUtil::getCovarianceForPose (HSL/map/OccGridMapUtil.h:106-160) + getCovMatrixWorldCoords (:162-189). The seven
+// sigma-point likelihoods come from k_residual; the 3x3 arithmetic follows Eigen 3.3's evaluation order (fp32, unfused):
+// likelihoods.sum() = (a0 + (a1 + a2)) + ((a3 + a4) + (a5 + a6)); mean += sigma_i * lh_i; cov += (lh_i * inv) * (d d^T).
+int hs_covariance_for_pose(hs_engine* e, int stream, int level, const float* pose_map, const float* points, int n_points,
+                           float* cov_map9, float* cov_world9) {
+  if (!pose_map || !cov_map9) return HS_ERR_INVALID_ARG;
+  const float dtx = 1.5f, dty = 1.5f, dang = 0.05f;
+  const float x = pose_map[0], y = pose_map[1], ang = pose_map[2];
+  volatile float sp[7][3] = {{x + dtx, y, ang}, {x - dtx, y, ang}, {x, y + dty, ang}, {x, y - dty, ang},
+                             {x, y, ang + dang}, {x, y, ang - dang}, {x, y, ang}};
+  float spf[21], lh[7];
+  for (int i = 0; i < 7; ++i) for (int k = 0; k < 3; ++k) spf[3 * i + k] = sp[i][k];
+  int st = hs_likelihood_batch(e, stream, level, spf, 7, points, n_points, nullptr, lh);
+  if (st != HS_OK) return st;
+  volatile float s12 = lh[1] + lh[2], s012 = lh[0] + s12, s34 = lh[3] + lh[4], s56 = lh[5] + lh[6], s3456 = s34 + s56;
+  volatile float sum = s012 + s3456;
+  volatile float inv = 1 / sum;
+  volatile float mean[3] = {0.0f, 0.0f, 0.0f};
+  for (int i = 0; i < 7; ++i)
+    for (int k = 0; k < 3; ++k) { volatile float t = sp[i][k] * lh[i]; mean[k] = mean[k] + t; }
+  for (int k = 0; k < 3; ++k) mean[k] = mean[k] * inv;
+  volatile float cov[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < 7; ++i) {
+    volatile float d[3] = {sp[i][0] - mean[0], sp[i][1] - mean[1], sp[i][2] - mean[2]};
+    volatile float w = lh[i] * inv;
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) { volatile float o = d[r] * d[c]; volatile float t = w * o; cov[3 * r + c] = cov[3 * r + c] + t; }
+  }
+  for (int k = 0; k < 9; ++k) cov_map9[k] = cov[k];
+  if (cov_world9) {
+    float res = e->cfg.map_resolution;
+    for (int i = 0; i < level; ++i) res *= 2.0f;          // getCellLength() of the level
+    volatile float scale = res, scale_sq = scale * scale;
+    for (int k = 0; k < 9; ++k) cov_world9[k] = 0.0f;
+    cov_world9[0] = cov[0] * scale_sq;
+    cov_world9[4] = cov[4] * scale_sq;
+    cov_world9[3] = cov[3] * scale_sq; cov_world9[1] = cov_world9[3];
+    cov_world9[6] = cov[6] * scale;    cov_world9[2] = cov_world9[6];
+    cov_world9[7] = cov[7] * scale;    cov_world9[5] = cov_world9[7];
+    cov_world9[8] = cov[8];
+  }
+  return HS_OK;
+}
+
+int hs_interp_map_value_batch(hs_engine* e, int stream, int level, const float* coords_map, int n, float* values_out, float* derivs_out) {
+  int st = check_stream_level(e, stream, level);
+  if (st != HS_OK) return st;
+  if (n < 0) return HS_ERR_INVALID_ARG;
+  if (n == 0) return HS_OK;
+  if (!coords_map) return HS_ERR_INVALID_ARG;
+  HS_CK(cudaSetDevice(e->device));
+  auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t b_in = (size_t)n * 2 * sizeof(float), b_out = (size_t)n * 4 * sizeof(float);
+  const size_t o_out = align(b_in);
+  if ((st = ensure_scratch(e, o_out + b_out)) != HS_OK) return st;
+  char* base = (char*)e->d_scratch;
+  HS_CK(cudaMemcpyAsync(base, coords_map, b_in, cudaMemcpyHostToDevice, e->stream));
+  e->h2d_bytes += b_in;
+  k_interp<<<(n + 127) / 128, 128, 0, e->stream>>>(e->P, stream, level, (const float2*)base, n, (float4*)(base + o_out));
+  HS_LAUNCHED(e);
+  std::vector<float> host((size_t)n * 4);
+  HS_CK(cudaMemcpyAsync(host.data(), base + o_out, b_out, cudaMemcpyDeviceToHost, e->stream));
+  e->d2h_bytes += b_out;
+  HS_CK(cudaStreamSynchronize(e->stream));
+  for (int i = 0; i < n; ++i) {
+    if (values_out) values_out[i] = host[4 * (size_t)i + 3];
+    if (derivs_out) { derivs_out[3 * (size_t)i] = host[4 * (size_t)i]; derivs_out[3 * (size_t)i + 1] = host[4 * (size_t)i + 1]; derivs_out[3 * (size_t)i + 2] = host[4 * (size_t)i + 2]; }
+  }
+  return HS_OK;
+}
+
+int hs_occupancy_ray_batch(hs_engine* e, int stream, int level, const int32_t* begin_cells, const int32_t* end_cells, int n,
+                           float* dist_out, int32_t* hit_cells_out) {
+  int st = check_stream_level(e, stream, level);
+  if (st != HS_OK) return st;
+  if (n < 0) return HS_ERR_INVALID_ARG;
+  if (n == 0) return HS_OK;
+  if (!begin_cells || !end_cells || !dist_out) return HS_ERR_INVALID_ARG;
+  HS_CK(cudaSetDevice(e->device));
+  auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t b_c = (size_t)n * 2 * sizeof(int32_t), b_d = (size_t)n * sizeof(float);
+  const size_t o_e = align(b_c), o_d = o_e + align(b_c), o_h = o_d + align(b_d);
+  if ((st = ensure_scratch(e, o_h + b_c)) != HS_OK) return st;
+  char* base = (char*)e->d_scratch;
+  HS_CK(cudaMemcpyAsync(base, begin_cells, b_c, cudaMemcpyHostToDevice, e->stream));
+  HS_CK(cudaMemcpyAsync(base + o_e, end_cells, b_c, cudaMemcpyHostToDevice, e->stream));
+  HS_CK(cudaMemsetAsync(base + o_h, 0xFF, b_c, e->stream));   // hit cells default to (-1, -1)
+  e->h2d_bytes += 2 * b_c;
+  k_occupancy_ray<<<(n + 127) / 128, 128, 0, e->stream>>>(e->P, stream, level, (const int2*)base, (const int2*)(base + o_e), n,
+                                                          (float*)(base + o_d), (int2*)(base + o_h));
+  HS_LAUNCHED(e);
+  HS_CK(cudaMemcpyAsync(dist_out, base + o_d, b_d, cudaMemcpyDeviceToHost, e->stream));
+  if (hit_cells_out) HS_CK(cudaMemcpyAsync(hit_cells_out, base + o_h, b_c, cudaMemcpyDeviceToHost, e->stream));
+  e->d2h_bytes += b_d + (hit_cells_out ? b_c : 0);
+  HS_CK(cudaStreamSynchronize(e->stream));
+  return HS_OK;
+}
+
+// Everything of one stream that is not a grid cell: with hs_download_level / hs_upload_level of every level this is a
+// complete checkpoint of a HectorSlamProcessor (the reference has none; GridMapBase::operator= copies a grid, GridMapBase.h:182-205).
+int hs_export_stream_state(hs_engine* e, int stream, hs_stream_state* out, float* coarse_points_out) {
+  if (!e || !out || stream < 0 || stream >= e->P.n_streams) return HS_ERR_INVALID_ARG;
+  HS_CK(cudaSetDevice(e->device));
+  const HsParams& P = e->P;
+  const size_t s = (size_t)stream;
+  HS_CK(cudaMemcpyAsync(out->last_scan_match_pose, P.last_pose + 3 * s, 3 * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  HS_CK(cudaMemcpyAsync(out->last_map_update_pose, P.last_update_pose + 3 * s, 3 * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  HS_CK(cudaMemcpyAsync(out->last_scan_match_cov, P.cov + 9 * s, 9 * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  HS_CK(cudaMemcpyAsync(&out->curr_update_index, P.cur_update_index + s, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  HS_CK(cudaMemcpyAsync(&out->last_update_index, P.last_update_index + s, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  HS_CK(cudaMemcpyAsync(&out->coarse_count, P.coarse_cnt + s, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  HS_CK(cudaMemcpyAsync(out->coarse_origo, P.coarse_origo + 2 * s, 2 * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  if (coarse_points_out)
+    HS_CK(cudaMemcpyAsync(coarse_points_out, P.coarse_pts + s * P.max_points * 2, (size_t)P.max_points * 2 * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  HS_CK(cudaStreamSynchronize(e->stream));
+  return HS_OK;
+}
+
+int hs_import_stream_state(hs_engine* e, int stream, const hs_stream_state* in, const float* coarse_points) {
+  if (!e || !in || stream < 0 || stream >= e->P.n_streams) return HS_ERR_INVALID_ARG;
+  if (in->coarse_count < 0 || in->coarse_count > e->P.max_points || (in->coarse_count > 0 && !coarse_points)) return HS_ERR_INVALID_ARG;
+  HS_CK(cudaSetDevice(e->device));
+  const HsParams& P = e->P;
+  const size_t s = (size_t)stream;
+  HS_CK(cudaMemcpyAsync(P.last_pose + 3 * s, in->last_scan_match_pose, 3 * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  HS_CK(cudaMemcpyAsync(P.last_update_pose + 3 * s, in->last_map_update_pose, 3 * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  HS_CK(cudaMemcpyAsync(P.cov + 9 * s, in->last_scan_match_cov, 9 * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  HS_CK(cudaMemcpyAsync(P.cur_update_index + s, &in->curr_update_index, sizeof(int), cudaMemcpyHostToDevice, e->stream));
+  HS_CK(cudaMemcpyAsync(P.last_update_index + s, &in->last_update_index, sizeof(int), cudaMemcpyHostToDevice, e->stream));
+  HS_CK(cudaMemcpyAsync(P.coarse_cnt + s, &in->coarse_count, sizeof(int), cudaMemcpyHostToDevice, e->stream));
+  HS_CK(cudaMemcpyAsync(P.coarse_origo + 2 * s, in->coarse_origo, 2 * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  if (coarse_points)
+    HS_CK(cudaMemcpyAsync(P.coarse_pts + s * P.max_points * 2, coarse_points, (size_t)P.max_points * 2 * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  HS_CK(cudaStreamSynchronize(e->stream));
+  return HS_OK;
+}
+
 // ---- map access ----------------------------------------------------------------------------------
 
 static int check_level(const hs_engine* e, int stream, int level) {

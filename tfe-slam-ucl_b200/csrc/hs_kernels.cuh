@@ -752,6 +752,124 @@ __global__ void __launch_bounds__(HS_MATCH_THREADS) k_hessian_derivs(HsParams P,
 }
 
 // ------------------------------------------------------------------------------------------------
+// Off-path OccGridMapUtil members (HSL/map/OccGridMapUtil.h:106-285) and the occupancy ray query of hector_map_tools.
+
+// OccGridMapUtil::interpMapValue (OccGridMapUtil.h:241-285): bilinear probability, 0 outside the map limits.
+__device__ __forceinline__ float hs_interp_map_value(const float* __restrict__ val, const HsLevel& L, float qx, float qy) {
+  if (!(qx >= 0.0f && qx <= L.limx && qy >= 0.0f && qy <= L.limy)) return 0.0f;
+  const int ix = (int)qx, iy = (int)qy;
+  const float fx = qx - (float)ix, fy = qy - (float)iy;
+  const float* p = val + iy * L.sx + ix;
+  const float i0 = hs_probability(__ldg(p)), i1 = hs_probability(__ldg(p + 1));
+  const float i2 = hs_probability(__ldg(p + L.sx)), i3 = hs_probability(__ldg(p + L.sx + 1));
+  const float x_inv = 1.0f - fx, y_inv = 1.0f - fy;
+  return ((i0 * x_inv + i1 * fx) * y_inv) + ((i2 * x_inv + i3 * fx) * fy);
+}
+
+// k_residual: getResidualForState / getLikelihoodForState (OccGridMapUtil.h:201-233) for many pose hypotheses against one
+// stream's level. One CTA per pose; the threads evaluate 1 - interpMapValue per point into shared memory, then the
+// residual is summed in the reference's point order (STRICT: one dependent FADD chain, bitwise the CPU result) or by a
+// tree. dynamic smem: n_pts floats.
+template <bool STRICT>
+__global__ void __launch_bounds__(HS_MATCH_THREADS) k_residual(HsParams P, int stream, int level, const float* __restrict__ poses_map, int n_poses,
+                                                               const float2* __restrict__ pts, int n_pts, float* __restrict__ residual_out,
+                                                               float* __restrict__ likelihood_out) {
+  extern __shared__ float hs_fun[];
+  const int k = blockIdx.x;
+  if (k >= n_poses) return;
+  const HsLevel& L = P.lv[level];
+  const float* val = P.val + (size_t)stream * P.cells_per_stream + L.cell_offset;
+  const float ex = poses_map[3 * k], ey = poses_map[3 * k + 1], th = poses_map[3 * k + 2];
+  const float sn = hs_sinf(th), cs = hs_cosf(th);
+  for (int i = threadIdx.x; i < n_pts; i += blockDim.x) {
+    const float2 p = pts[i];
+    const float qx = (cs * p.x + (-sn) * p.y) + ex;
+    const float qy = (sn * p.x + cs * p.y) + ey;
+    hs_fun[i] = 1.0f - hs_interp_map_value(val, L, qx, qy);
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float residual = 0.0f;
+    if (STRICT) {
+      if (threadIdx.x == 0) {
+        int i = 0;
+        for (; i + 8 <= n_pts; i += 8) {
+          const float t0 = hs_fun[i], t1 = hs_fun[i + 1], t2 = hs_fun[i + 2], t3 = hs_fun[i + 3];
+          const float t4 = hs_fun[i + 4], t5 = hs_fun[i + 5], t6 = hs_fun[i + 6], t7 = hs_fun[i + 7];
+          residual += t0; residual += t1; residual += t2; residual += t3; residual += t4; residual += t5; residual += t6; residual += t7;
+        }
+        for (; i < n_pts; ++i) residual += hs_fun[i];
+      }
+    } else {
+      for (int i = threadIdx.x; i < n_pts; i += 32) residual += hs_fun[i];
+#pragma unroll
+      for (int m = 16; m >= 1; m >>= 1) residual += __shfl_xor_sync(0xffffffffu, residual, m);
+    }
+    if (threadIdx.x == 0) {
+      residual_out[k] = residual;
+      const float sizef = (float)n_pts;                 // getLikelihoodForResidual (OccGridMapUtil.h:208-214)
+      likelihood_out[k] = 1.0f - (residual / sizef);
+    }
+  }
+}
+
+// k_interp: interpMapValueWithDerivatives / interpMapValue (OccGridMapUtil.h:241-347) at arbitrary map coordinates of one
+// stream's level; out4 [n][4] = (value, d/dx, d/dy, interpMapValue) -- the first three are the reference's Vector3f.
+__global__ void __launch_bounds__(128) k_interp(HsParams P, int stream, int level, const float2* __restrict__ coords, int n, float4* __restrict__ out4) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const HsLevel& L = P.lv[level];
+  const float* val = P.val + (size_t)stream * P.cells_per_stream + L.cell_offset;
+  const float2 c = coords[i];
+  float gx, gy, rot, fv;
+  HsCellCache none;
+  hs_point_terms<false>(val, L, c.x, c.y, 0.0f, 1.0f, 0.0f, 0.0f, none, gx, gy, rot, fv);   // identity rotation: q = (0,0) + (ex,ey)
+  const float m = hs_interp_map_value(val, L, c.x, c.y);
+  out4[i] = make_float4(m, gx, gy, m);
+}
+
+// k_occupancy_ray: HectorMapTools::DistanceMeasurementProvider::checkOccupancyBresenhami + bresenham2D
+// (src/hector_slam/hector_map_tools/include/hector_map_tools/HectorMapTools.h:148-232) for many rays on one stream's
+// level. The reference walks the published int8 grid, where a cell is 100 exactly when its log-odds are > 0
+// (HectorMappingRos.cpp:447-470), so the walk tests the log-odds plane directly. One thread per ray:
+// dist_out = (float)(int)|begin - hit| in cells or -1, hit_out = hit cell (untouched on a miss).
+__global__ void __launch_bounds__(128) k_occupancy_ray(HsParams P, int stream, int level, const int2* __restrict__ begins, const int2* __restrict__ ends,
+                                                       int n, float* __restrict__ dist_out, int2* __restrict__ hit_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const HsLevel& L = P.lv[level];
+  const float* val = P.val + (size_t)stream * P.cells_per_stream + L.cell_offset;
+  const int sx = L.sx, sy = L.sy;
+  const int x0 = begins[i].x, y0 = begins[i].y, x1 = ends[i].x, y1 = ends[i].y;
+  float d = -1.0f;
+  if (x0 >= 0 && x0 < sx && y0 >= 0 && y0 < sy && x1 >= 0 && x1 < sx && y1 >= 0 && y1 < sy) {
+    const int dx = x1 - x0, dy = y1 - y0;
+    const unsigned abs_dx = (unsigned)abs(dx), abs_dy = (unsigned)abs(dy);
+    const int off_dx = dx > 0 ? 1 : -1, off_dy = (dy > 0 ? 1 : -1) * sx;
+    unsigned abs_da, abs_db;
+    int off_a, off_b;
+    if (abs_dx >= abs_dy) { abs_da = abs_dx; abs_db = abs_dy; off_a = off_dx; off_b = off_dy; }
+    else { abs_da = abs_dy; abs_db = abs_dx; off_a = off_dy; off_b = off_dx; }
+    int err = (int)(abs_da / 2);
+    int offset = y0 * sx + x0;
+    const unsigned end = abs_da < 5000u ? abs_da : 5000u;   // bresenham2D's max_length argument is the constant 5000 (:189,:193)
+    for (unsigned t = 0; t < end; ++t) {
+      if (__ldg(val + offset) > 0.0f) {     // data[offset] == 100
+        const int hx = offset % sx, hy = offset / sx;
+        const float fx = (float)(x0 - hx), fy = (float)(y0 - hy);
+        d = (float)(int)sqrtf(fx * fx + fy * fy);
+        hit_out[i] = make_int2(hx, hy);
+        break;
+      }
+      offset += off_a;
+      err += (int)abs_db;
+      if ((unsigned)err >= abs_da) { offset += off_b; err -= (int)abs_da; }
+    }
+  }
+  dist_out[i] = d;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Integration: OccGridMapBase::updateByScan / updateLineBresenhami / bresenham2D / bresenhamCellFree /
 // bresenhamCellOcc (HSL/map/OccGridMapBase.h:121-260) + the log-odds updates (GridMapLogOdds.h:135-156).
 //
