@@ -151,6 +151,16 @@ int hs_match_batch(hs_engine* e, int n, const int32_t* stream_ids, const float* 
 int hs_raycast_batch(hs_engine* e, int n, const int32_t* stream_ids, const float* points, const int32_t* counts,
                      const float* origos, const float* poses_world);
 
+/* nav_msgs/OccupancyGrid metadata of a level as HectorMappingRos::setServiceGetMapData fills it
+ * (HectorMappingRos.cpp:544-560): origin = getWorldCoords(0,0) - cellLength/2, resolution = getCellLength(), width/height
+ * = grid size. With hs_classify_level this is the published map. */
+typedef struct {
+  float origin_x, origin_y;   /* info.origin.position [m] (orientation is identity) */
+  float resolution;           /* info.resolution [m/cell] */
+  int32_t width, height;      /* info.width, info.height [cells] */
+} hs_map_info;
+int hs_get_map_info(const hs_engine* e, int level, hs_map_info* out);
+
 /* Off-path members of OccGridMapUtil (HSL/map/OccGridMapUtil.h:106-285; not called by update(), used for relocalisation
  * scoring). Poses are MAP coordinates of the level, points already scaled to it; all host pointers.
  * getResidualForState (:216-233) and getLikelihoodForState (:201-214) for n_poses hypotheses; either output may be NULL. */

@@ -79,8 +79,33 @@ def kernels(tag, rep):
                 f.write("```\n")
 
 
+def traffic(tag, reps, streams_per_launch=1024):
+    """profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per launch of the hot kernels (bench.py's
+    roofline.traffic reads it when the workload matches)."""
+    import json
+    out = {"source": "profiles/%s_*.md: ncu --set full --clock-control none, bench.py --steps 4 --warmup 3 (%d streams, one launch each)" % (tag, streams_per_launch),
+           "streams_per_launch": streams_per_launch, "kernels": {}}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for rep in reps:
+        raw = ncu_csv(rep, "raw")
+        hdr, units = raw[0], raw[1]
+        idx = {h: i for i, h in enumerate(hdr)}
+        for r in raw[2:]:
+            name = r[idx["Kernel Name"]].split("(")[0].replace("void ", "").split("<")[0]
+            key = "k_match" if name.startswith("k_match") else name
+            if key in out["kernels"]:
+                continue
+            rd = float(r[idx["dram__bytes_read.sum"]]) * scale[units[idx["dram__bytes_read.sum"]]]
+            wr = float(r[idx["dram__bytes_write.sum"]]) * scale[units[idx["dram__bytes_write.sum"]]]
+            out["kernels"][key] = {"dram_bytes_per_launch": rd + wr, "dram_read": rd, "dram_write": wr,
+                                   "gpu_time_us_under_ncu": float(r[idx["gpu__time_duration.sum"]])}
+    with open(os.path.join(HERE, "traffic.json"), "w") as f:
+        json.dump(out, f, indent=1)
+
+
 if __name__ == "__main__":
     tag = sys.argv[1]
     launches(tag, sys.argv[2])
     for rep in sys.argv[3:]:
         kernels(tag, rep)
+    traffic(tag, sys.argv[3:])

@@ -171,6 +171,21 @@ def test_teacher_forced_bands_all_octants(hs, oracle):
             p.close()
 
 
+def test_published_map_info_matches_reference_geometry(hs, oracle):
+    """setServiceGetMapData (HectorMappingRos.cpp:544-560): origin = getWorldCoords(0,0) - cellLength/2 per level."""
+    for res, size, start, levels in ((0.05, 1024, (0.5, 0.5), 3), (0.025, 2048, (0.3, 0.7), 4), (0.1, 500, (0.5, 0.5), 2)):
+        p = oracle.CpuProcessor("port", res, size, size, start, levels)
+        with hs.Engine(res, size, size, start, levels, n_streams=1, max_points=8) as eng:
+            for l in range(levels):
+                mi = eng.map_info(l)
+                sx, sy, cl = p.level_dims(l)
+                w0 = p.map_to_world(l, np.zeros(3, np.float32))
+                half = np.float32(cl) * np.float32(0.5)
+                assert mi["width"] == sx and mi["height"] == sy and np.float32(mi["resolution"]) == np.float32(cl)
+                assert np.float32(mi["origin"][0]) == np.float32(w0[0]) - half and np.float32(mi["origin"][1]) == np.float32(w0[1]) - half
+        p.close()
+
+
 def test_upload_download_classify_roundtrip(hs):
     with hs.Engine(0.05, 64, 64, (0.5, 0.5), 2, n_streams=2, max_points=8) as eng:
         rng = np.random.default_rng(0)

@@ -48,6 +48,11 @@ class HsStats(ctypes.Structure):
                 ("cell_visits", ctypes.c_uint64)]
 
 
+class HsMapInfo(ctypes.Structure):
+    _fields_ = [("origin_x", ctypes.c_float), ("origin_y", ctypes.c_float), ("resolution", ctypes.c_float),
+                ("width", ctypes.c_int32), ("height", ctypes.c_int32)]
+
+
 class HsStreamState(ctypes.Structure):
     _fields_ = [("last_scan_match_pose", ctypes.c_float * 3), ("last_map_update_pose", ctypes.c_float * 3),
                 ("last_scan_match_cov", ctypes.c_float * 9), ("curr_update_index", ctypes.c_int32),
@@ -117,7 +122,7 @@ def lib():
         "hs_raycast_batch": (_I, [_P, _I, _P, _P, _P, _P, _P]),
         "hs_download_level": (_I, [_P, _I, _I, _P]), "hs_upload_level": (_I, [_P, _I, _I, _P]),
         "hs_get_update_index": (_I, [_P, _I, _I, _P]), "hs_classify_level": (_I, [_P, _I, _I, _P]),
-        "hs_get_stats": (_I, [_P, _P]),
+        "hs_get_stats": (_I, [_P, _P]), "hs_get_map_info": (_I, [_P, _I, _P]),
         "hs_likelihood_batch": (_I, [_P, _I, _I, _P, _I, _P, _I, _P, _P]),
         "hs_covariance_for_pose": (_I, [_P, _I, _I, _P, _P, _I, _P, _P]),
         "hs_interp_map_value_batch": (_I, [_P, _I, _I, _P, _I, _P, _P]),
@@ -410,6 +415,12 @@ class Engine:
         v = ctypes.c_int()
         _check(lib().hs_get_update_index(self._h, stream, level, ctypes.byref(v)), "hs_get_update_index")
         return v.value
+
+    def map_info(self, level=0):
+        """nav_msgs/OccupancyGrid metadata of a level (HectorMappingRos::setServiceGetMapData)."""
+        mi = HsMapInfo()
+        _check(lib().hs_get_map_info(self._h, level, ctypes.byref(mi)), "hs_get_map_info")
+        return {"origin": (mi.origin_x, mi.origin_y), "resolution": mi.resolution, "width": mi.width, "height": mi.height}
 
     def classify_level(self, stream, level):
         sx, sy, _ = self.level_dims(level)

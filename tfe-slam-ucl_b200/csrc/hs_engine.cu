@@ -950,6 +950,23 @@ int hs_classify_level(hs_engine* e, int stream, int level, int8_t* occupancy_out
   return HS_OK;
 }
 
+// HectorMappingRos::setServiceGetMapData (HectorMappingRos.cpp:544-560): origin = getWorldCoords(0,0) - cellLength/2.
+int hs_get_map_info(const hs_engine* e, int level, hs_map_info* out) {
+  if (!e || !out || level < 0 || level >= e->P.n_levels) return HS_ERR_INVALID_ARG;
+  const HsLevel& L = e->P.lv[level];
+  float res = e->cfg.map_resolution;
+  for (int i = 0; i < level; ++i) res *= 2.0f;
+  volatile float zx = L.a * 0.0f, zy = L.a * 0.0f;
+  volatile float ox = zx + L.twx, oy = zy + L.twy;     // worldTmap * (0, 0)
+  volatile float half = res * 0.5f;
+  out->origin_x = ox - half;
+  out->origin_y = oy - half;
+  out->resolution = res;
+  out->width = L.sx;
+  out->height = L.sy;
+  return HS_OK;
+}
+
 int hs_get_stats(hs_engine* e, hs_stats* out) {
   if (!e || !out) return HS_ERR_INVALID_ARG;
   HS_CK(cudaSetDevice(e->device));
