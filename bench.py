@@ -263,8 +263,26 @@ def main():
         run_host(k)   # returns when this step's poses are valid in host memory
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    clocks = sampler.finish()      # sampled across both timed legs (device-resident and end-to-end)
     pose_checksum = float(h_pose.sum())
+
+    # ---- leg 2b (informational): the same, but the caller hands over LaserScan ranges and the engine does
+    # rosLaserScanToDataContainer on the GPU (hs_update_batch_ranges): half the host-to-device bytes
+    eng.reset()
+    ranges_all, _ = hs.scangen_batch(sc, 0xC0FFEE + first_stream, S, 0, steps, truth=False)
+    eng.set_scan_geometry(sc.n_beams, sc.angle_min, sc.angle_increment, sc.range_min, sc.range_max)
+    h_rng = torch.from_numpy(ranges_all).pin_memory()
+    rng_step = h_rng[0].numel() * 4
+    for k in range(W):
+        eng.update_batch_ranges_raw(S, h_rng.data_ptr() + k * rng_step, h_pose.data_ptr())
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(W, W + K):
+        eng.update_batch_ranges_raw(S, h_rng.data_ptr() + k * rng_step, h_pose.data_ptr())
+    torch.cuda.synchronize()
+    e2e_rng_s = time.perf_counter() - t0
+    e2e_rng_scans, e2e_rng_max_s = sharding.aggregate_throughput(S * K, e2e_rng_s, device="cuda")
+    ranges_checksum = float(h_pose.sum())
+    clocks = sampler.finish()      # sampled across all timed legs (device-resident and end-to-end)
     e2e_scans, e2e_max_s = sharding.aggregate_throughput(S * K, e2e_s, device="cuda")
     e2e_value = e2e_scans / e2e_max_s
     h2d_step = pts_step + cnt_step
@@ -314,7 +332,10 @@ def main():
                "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "f32", "data": "synthetic", "config": config, "impl": "ours",
                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step,
-                       "api": "hs_update_batch (host pointers, pinned)", "pose_checksum": pose_checksum},
+                       "api": "hs_update_batch (host pointers, pinned)", "pose_checksum": pose_checksum,
+                       "ranges_api": {"value": e2e_rng_scans / e2e_rng_max_s, "h2d_bytes_per_step": rng_step, "d2h_bytes_per_step": d2h_step,
+                                      "api": "hs_update_batch_ranges (LaserScan ranges in, conversion on the GPU)",
+                                      "pose_checksum": ranges_checksum}},
                "gpu_launches": int(agg[2].item()),
                "integrated_scans": int(agg[0].item()), "scans": world * S * K,
                "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,

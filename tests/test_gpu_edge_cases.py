@@ -306,3 +306,39 @@ def test_offpath_members_on_random_maps(hs, oracle):
                 d_ref, h_ref = oracle.check_occupancy_bresenhami("port", occ_sparse, begins[i], ends[i])
                 assert dist[i] == d_ref and np.array_equal(hit[i], h_ref if h_ref is not None else (-1, -1)), i
         p.close()
+
+
+def test_pinned_host_batches_are_chunked_and_identical(hs, monkeypatch):
+    """With pinned host buffers hs_update_batch cuts the batch into chunks on several CUDA streams (copy of chunk c+1 under
+    the kernels of chunk c). Results must not depend on the chunking: 1, 2, 3 and 4 chunks, with and without stream_ids."""
+    import torch
+    n, n_scans = 300, 5
+    sc, ranges, pts, cnt, truth = make_streams(hs, n, n_scans, seed0=9000)
+    h_pts = torch.from_numpy(pts).pin_memory()
+    h_cnt = torch.from_numpy(cnt).pin_memory()
+    ids = torch.from_numpy(np.random.default_rng(3).permutation(n).astype(np.int32)).pin_memory()
+    results = []
+    for chunks in ("1", "2", "3", "4"):
+        monkeypatch.setenv("HSGPU_E2E_CHUNKS", chunks)
+        for use_ids in (False, True):
+            with hs.Engine(n_streams=n, max_points=360) as eng:
+                eng.set_update_factor_free(0.4); eng.set_update_factor_occupied(0.9)
+                eng.set_map_update_min_dist_diff(0.0); eng.set_map_update_min_angle_diff(0.0)
+                out = torch.empty((n_scans, n, 3), dtype=torch.float32).pin_memory()
+                for k in range(n_scans):
+                    eng.update_batch_raw(n, h_pts[k].data_ptr(), h_cnt[k].data_ptr(), out[k].data_ptr(),
+                                         ids_ptr=ids.data_ptr() if use_ids else None)
+                poses = out.numpy().copy()
+                if use_ids:   # slot i updated stream ids[i]: bring back to stream order
+                    inv = np.empty(n, np.int64); inv[ids.numpy()] = np.arange(n)
+                    final = eng.poses()
+                    maps = [eng.download_level(int(ids[s]), 0)["logOddsVal"].copy() for s in (0, n // 2, n - 1)]
+                else:
+                    final = eng.poses()
+                    maps = [eng.download_level(s, 0)["logOddsVal"].copy() for s in (0, n // 2, n - 1)]
+                results.append((chunks, use_ids, poses, final, maps))
+    base = results[0]
+    for chunks, use_ids, poses, final, maps in results[1:]:
+        assert np.array_equal(bits(poses), bits(base[2])), (chunks, use_ids)     # slot i always carries scan stream i's points
+        for a, b in zip(maps, base[4]):
+            assert np.array_equal(bits(a), bits(b)), (chunks, use_ids)

@@ -29,7 +29,7 @@ t = (t - t0) / 1e3   # us
 names = ["setup+A1", "A2+A3", "B1", "B2", "C"]
 print("kernel span %.1f us, CTAs %d" % (t[:, 5].max(), len(t)))
 for lvl in range(3):
-    tl = t[lvl * S:(lvl + 1) * S]
+    tl = t[lvl::3]
     d = np.diff(tl, axis=1)
     print("level %d: CTA life mean %.1f us | " % (lvl, (tl[:, 5] - tl[:, 0]).mean()) + "  ".join("%s %.2f" % (n, d[:, i].mean()) for i, n in enumerate(names)))
 # how many CTAs are inside each phase over time (sampled every 2 us)

@@ -15,12 +15,18 @@
 #include "hs_kernels.cuh"
 #include "hsgpu.h"
 
+#define HS_MAX_CHUNKS 4
+
 struct hs_engine {
   hs_config cfg;
   HsParams P;
   int device;
   cudaStream_t own_stream;
   cudaStream_t stream;
+  // host batches are cut into chunks whose host-to-device copies overlap the kernels of the previous chunk
+  int e2e_chunks;
+  cudaStream_t aux_stream[HS_MAX_CHUNKS - 1];
+  cudaEvent_t ev_fork, ev_join[HS_MAX_CHUNKS - 1];
   // staging (device) for the host-pointer entry points
   float* d_points;
   int32_t* d_counts;
@@ -266,6 +272,20 @@ int hs_create(const hs_config* cfg, hs_engine** out) {
   }
   e->stream = e->own_stream;
   {
+    e->e2e_chunks = 2;   // measured on B200 (1024 streams x 360 points, pinned buffers): see DESIGN.md section 5
+    if (const char* c = getenv("HSGPU_E2E_CHUNKS")) e->e2e_chunks = atoi(c);
+    e->e2e_chunks = e->e2e_chunks < 1 ? 1 : (e->e2e_chunks > HS_MAX_CHUNKS ? HS_MAX_CHUNKS : e->e2e_chunks);
+    cudaError_t err = cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming);
+    for (int c = 0; c < HS_MAX_CHUNKS - 1 && err == cudaSuccess; ++c) {
+      err = cudaStreamCreateWithFlags(&e->aux_stream[c], cudaStreamNonBlocking);
+      if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e->ev_join[c], cudaEventDisableTiming);
+    }
+    if (err != cudaSuccess) {
+      hs_destroy(e);
+      return (int)err;
+    }
+  }
+  {
     int smem = cfg->max_points * HS_NPROD * (int)sizeof(float);  // k_match's per-CTA product buffer
     if (smem > 48 * 1024) {
       cudaError_t e1 = cudaFuncSetAttribute(k_match<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -336,6 +356,11 @@ int hs_destroy(hs_engine* e) {
                   e->d_beam_cs, e->d_scratch};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  for (int c = 0; c < HS_MAX_CHUNKS - 1; ++c) {
+    if (e->aux_stream[c]) { cudaStreamSynchronize(e->aux_stream[c]); cudaStreamDestroy(e->aux_stream[c]); }
+    if (e->ev_join[c]) cudaEventDestroy(e->ev_join[c]);
+  }
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
   if (e->prof_events) {
     for (cudaEvent_t ev : *e->prof_events) cudaEventDestroy(ev);
@@ -426,24 +451,35 @@ static int check_batch(const hs_engine* e, int n) {
 }
 
 // match (+gate) then ray-cast, all pointers on the device
+// Slots [slot0, slot0 + n) of the batch on CUDA stream `st` (the engine's stream, or one of its auxiliary streams when a
+// host batch is cut into chunks); the pointers are those of the WHOLE batch.
 static int run_update_device(hs_engine* e, int n, const int32_t* ids, const float* points, const int32_t* counts,
-                             const float* origos, const float* hints, const uint8_t* flags, int mode) {
+                             const float* origos, const float* hints, const uint8_t* flags, int mode,
+                             cudaStream_t st = nullptr, int slot0 = 0) {
   if (n == 0) return HS_OK;
+  if (!st) st = e->stream;
+  HsParams Pc = e->P;
+  Pc.slot0 = slot0;
+  struct StreamSwap {   // ProfScope records on e->stream
+    hs_engine* e; cudaStream_t saved;
+    StreamSwap(hs_engine* en, cudaStream_t s) : e(en), saved(en->stream) { e->stream = s; }
+    ~StreamSwap() { e->stream = saved; }
+  } swap(e, st);
   {
     ProfScope ps(e, HS_K_MATCH);
     const int threads = HS_MATCH_THREADS;
     if (e->match_v2) {
       const size_t smem2 = match2_smem_for(e->P.max_points);
       if (e->P.strict)
-        k_match2<true><<<n, threads, smem2, e->stream>>>(e->P, n, ids, (const float2*)points, counts, (const float2*)origos, hints, flags, mode);
+        k_match2<true><<<n, threads, smem2, st>>>(Pc, n, ids, (const float2*)points, counts, (const float2*)origos, hints, flags, mode);
       else
-        k_match2<false><<<n, threads, smem2, e->stream>>>(e->P, n, ids, (const float2*)points, counts, (const float2*)origos, hints, flags, mode);
+        k_match2<false><<<n, threads, smem2, st>>>(Pc, n, ids, (const float2*)points, counts, (const float2*)origos, hints, flags, mode);
     } else {
     const size_t smem = (size_t)e->P.max_points * HS_NPROD * sizeof(float);
     int ppt = (e->P.max_points + threads - 1) / threads;   // register-resident points (+ cell caches) per thread
     ppt = ppt <= 2 ? 2 : (ppt <= 3 ? 3 : (ppt <= 6 ? 6 : 0));
 #define HS_LAUNCH_MATCH(STRICT_, PPT_)                                                               \
-  k_match<STRICT_, PPT_><<<n, threads, smem, e->stream>>>(e->P, n, ids, (const float2*)points, counts, \
+  k_match<STRICT_, PPT_><<<n, threads, smem, st>>>(Pc, n, ids, (const float2*)points, counts, \
                                                         (const float2*)origos, hints, flags, mode)
 #define HS_LAUNCH_MATCH_S(STRICT_)                                    \
   do {                                                                \
@@ -461,8 +497,8 @@ static int run_update_device(hs_engine* e, int n, const int32_t* ids, const floa
   if (mode == 0) {
     {
       ProfScope ps(e, HS_K_RAYCAST);
-      k_raycast<<<n * e->P.n_levels, HS_RAYCAST_THREADS, raycast_smem(e), e->stream>>>(
-          e->P, n, ids, (const float2*)points, counts, (const float2*)origos, raycast_log2_hash(e->P.max_points), e->log2_seg_levels);
+      k_raycast<<<n * e->P.n_levels, HS_RAYCAST_THREADS, raycast_smem(e), st>>>(
+          Pc, n, ids, (const float2*)points, counts, (const float2*)origos, raycast_log2_hash(e->P.max_points), e->log2_seg_levels);
     }
     HS_LAUNCHED(e);
   }
@@ -525,13 +561,36 @@ static int update_host(hs_engine* e, int n, const int32_t* ids, const float* poi
   if (!points || !counts) return HS_ERR_INVALID_ARG;
   if ((st = check_ids(e, n, ids)) != HS_OK) return st;
   HS_CK(cudaSetDevice(e->device));
-  size_t pbytes = (size_t)n * e->P.max_points * 2 * sizeof(float);
-  HS_CK(cudaMemcpyAsync(e->d_points, points, pbytes, cudaMemcpyHostToDevice, e->stream));
-  e->h2d_bytes += pbytes;
+  const size_t row = (size_t)e->P.max_points * 2;   // floats per slot
+  const size_t pbytes = (size_t)n * row * sizeof(float);
   if ((st = stage_common(e, n, ids, counts, origos, hints, flags)) != HS_OK) return st;
-  st = run_update_device(e, n, ids ? e->d_ids : nullptr, e->d_points, e->d_counts, origos ? e->d_origos : nullptr,
-                         hints ? e->d_hints : nullptr, flags ? e->d_flags : nullptr, mode);
-  if (st != HS_OK) return st;
+  // The points are the bulk of the input (2.9 KB per 360-beam scan). With pinned host memory the batch is cut into chunks:
+  // chunk c+1's copy runs on the copy engine while chunk c is matched and ray-cast (streams are independent, so the
+  // chunks' kernels may also overlap each other). Pageable memory is copied in one piece (its copies are staged anyway).
+  int chunks = 1;
+  if (e->e2e_chunks > 1 && n >= 64 * e->e2e_chunks) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, points) == cudaSuccess && attr.type == cudaMemoryTypeHost) chunks = e->e2e_chunks;
+    cudaGetLastError();
+  }
+  const int32_t* d_ids = ids ? e->d_ids : nullptr;
+  const float* d_or = origos ? e->d_origos : nullptr;
+  const float* d_hi = hints ? e->d_hints : nullptr;
+  const uint8_t* d_fl = flags ? e->d_flags : nullptr;
+  if (chunks > 1) HS_CK(cudaEventRecord(e->ev_fork, e->stream));   // after the small arrays and everything queued before
+  for (int c = 0; c < chunks; ++c) {
+    const int off = (int)((long long)n * c / chunks), cnt = (int)((long long)n * (c + 1) / chunks) - off;
+    cudaStream_t cs = c == 0 ? e->stream : e->aux_stream[c - 1];
+    if (c > 0) HS_CK(cudaStreamWaitEvent(cs, e->ev_fork, 0));
+    HS_CK(cudaMemcpyAsync(e->d_points + off * row, points + off * row, (size_t)cnt * row * sizeof(float), cudaMemcpyHostToDevice, cs));
+    st = run_update_device(e, cnt, d_ids, e->d_points, e->d_counts, d_or, d_hi, d_fl, mode, cs, off);
+    if (st != HS_OK) return st;
+    if (c > 0) {
+      HS_CK(cudaEventRecord(e->ev_join[c - 1], cs));
+      HS_CK(cudaStreamWaitEvent(e->stream, e->ev_join[c - 1], 0));
+    }
+  }
+  e->h2d_bytes += pbytes;
   if ((st = fetch_rows(e, e->P.last_pose, ids ? e->d_ids : nullptr, 0, n, 3, poses_out)) != HS_OK) return st;
   if (cov_out) {
     if (ids && poses_out) HS_CK(cudaStreamSynchronize(e->stream));  // d_out is reused by the second gather

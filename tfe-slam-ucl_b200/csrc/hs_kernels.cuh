@@ -39,6 +39,7 @@ struct HsParams {
   int n_levels;
   int n_streams;
   int max_points;
+  int slot0;                        // first slot of this launch (a host batch may be cut into chunks that run on several CUDA streams)
   int dbg_skip;                     // timing experiments only (HSGPU_DEBUG_SKIP): bit0 skip walk, bit1 skip sweep, bit2 skip end points
   unsigned long long* dbg_times;    // timing experiments only (HSGPU_DEBUG_TIMES): 8 globaltimer stamps per ray-cast CTA
   int strict;                       // 1: accumulate H/dTr in the reference's sequential point order
@@ -382,16 +383,18 @@ __device__ __forceinline__ void hs_match_tail(const HsParams& P, int slot, int s
 // dynamic shared memory: max_points * 9 floats.
 #define HS_MATCH_THREADS 128   // measured on B200 at 1024 streams: 64 -> 160 us, 96 -> 122, 128 -> 109, 192/256 -> 143 per launch
 
+// 7 CTAs per SM (<= 72 registers) keeps all 1024 streams of BASELINE configs[1] resident in ONE wave on 148 SMs; at 73+
+// registers the launch needs a second wave and takes 1.5x as long (measured: 94 -> 140 us).
 template <bool STRICT, int PPT>
-__global__ void __launch_bounds__(HS_MATCH_THREADS) k_match(HsParams P, int n_slots, const int32_t* __restrict__ stream_ids,
+__global__ void __launch_bounds__(HS_MATCH_THREADS, (PPT > 0 && PPT <= 3) ? 7 : 1) k_match(HsParams P, int n_slots, const int32_t* __restrict__ stream_ids,
                                                             const float2* __restrict__ points, const int32_t* __restrict__ counts,
                                                             const float2* __restrict__ origos, const float* __restrict__ hints,
                                                             const uint8_t* __restrict__ mwm_flags, int mode) {
   extern __shared__ float hs_prod[];
   __shared__ float s_est[5];  // ex, ey, eth, sin(eth), cos(eth)
-  const int slot = blockIdx.x;
+  const int slot = P.slot0 + blockIdx.x;
   const int tid = threadIdx.x;
-  if (slot >= n_slots) return;
+  if ((int)blockIdx.x >= n_slots) return;
   // the serial part (sums, 3x3 solve, sin/cos) is carried by ONE warp; which one rotates with the CTA index, so that the
   // serial warps of the CTAs sharing an SM sit on different SM sub-partitions (warp w issues from scheduler w mod 4)
   const int sw = blockIdx.x & ((blockDim.x >> 5) - 1);
@@ -625,9 +628,9 @@ __global__ void __launch_bounds__(HS_MATCH_THREADS) k_match2(HsParams P, int n_s
   float2* spts = reinterpret_cast<float2*>(pcache + P.max_points);
   int* kcell = reinterpret_cast<int*>(spts + P.max_points);
   unsigned short* miss = reinterpret_cast<unsigned short*>(kcell + P.max_points);
-  const int slot = blockIdx.x;
+  const int slot = P.slot0 + blockIdx.x;
   const int tid = threadIdx.x;
-  if (slot >= n_slots) return;
+  if ((int)blockIdx.x >= n_slots) return;
   // the serial part (sums, 3x3 solve, sin/cos) is carried by ONE warp; which one rotates with the CTA index, so that the
   // serial warps of the CTAs sharing an SM sit on different SM sub-partitions (warp w issues from scheduler w mod 4)
   const int sw = blockIdx.x & ((blockDim.x >> 5) - 1);
@@ -1035,13 +1038,16 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS, 3) k_raycast(HsParams P, i
   // is 20 % slower)
   int level, slot;
   {
-    slot = blockIdx.x / P.n_levels;
-    level = blockIdx.x - slot * P.n_levels;
+    const int local = blockIdx.x / P.n_levels;
+    level = blockIdx.x - local * P.n_levels;
+    slot = P.slot0 + local;
+    if (local >= n_slots) return;
   }
-  if (slot >= n_slots) return;
   hs_stamp(P, 0);
-  if (!P.slot_integrate[slot]) return;
-  int s = hs_slot_stream(stream_ids, slot);
+  // Everything this CTA needs from global memory is requested up front, BEFORE the gate flag is tested: the loads are
+  // independent, so the prologue costs one memory round trip instead of a chain of three (flag -> parameters -> points).
+  const int integrate = P.slot_integrate[slot];
+  const int s = hs_slot_stream(stream_ids, slot);
   const HsLevel& L = P.lv[level];
   float* val = P.val + (size_t)s * P.cells_per_stream + L.cell_offset;
   int* idx = P.idx + (size_t)s * P.cells_per_stream + L.cell_offset;
@@ -1056,7 +1062,6 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS, 3) k_raycast(HsParams P, i
   if (level == 0) {
     pts = points + (size_t)slot * P.max_points;
     n = counts[slot];
-    n = n < 0 ? 0 : (n > P.max_points ? P.max_points : n);
     float2 o = origos ? origos[slot] : make_float2(0.f, 0.f);
     ox = o.x; oy = o.y;
   } else {
@@ -1065,13 +1070,17 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS, 3) k_raycast(HsParams P, i
     ox = P.coarse_origo[2 * s] * L.pt_factor;
     oy = P.coarse_origo[2 * s + 1] * L.pt_factor;
   }
+  const float2 p_first = (int)threadIdx.x < P.max_points ? pts[threadIdx.x] : make_float2(0.f, 0.f);   // this thread's first beam
   const int mark_base = P.slot_mark_base[slot];
+  const float pose_x = P.slot_pose[3 * slot], pose_y = P.slot_pose[3 * slot + 1];
+  const float sn = P.slot_sc[2 * slot], cs = P.slot_sc[2 * slot + 1];   // sinf / cosf of the pose angle, from the gate
+  if (!integrate) return;
+  n = n < 0 ? 0 : (n > P.max_points ? P.max_points : n);
   const int mark_free = mark_base + 1, mark_occ = mark_base + 2;
   const float f = P.log_odds_free, o = P.log_odds_occ;
 
   float mpx, mpy;
-  hs_world_to_map(L, P.slot_pose[3 * slot], P.slot_pose[3 * slot + 1], mpx, mpy);
-  const float sn = P.slot_sc[2 * slot], cs = P.slot_sc[2 * slot + 1];   // sinf / cosf of the pose angle, from the gate
+  hs_world_to_map(L, pose_x, pose_y, mpx, mpy);
   const int bx = (int)(((cs * ox + (-sn) * oy) + mpx) + 0.5f);  // Vector2i(float, float): truncation (OccGridMapBase.h:137)
   const int by = (int)(((sn * ox + cs * oy) + mpy) + 0.5f);
   const float pf = L.pt_factor;
@@ -1094,7 +1103,7 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS, 3) k_raycast(HsParams P, i
     unsigned visits = 0;
     int xmin = INT_MAX, ymin = INT_MAX, xmax = INT_MIN, ymax = INT_MIN;
     for (int i = threadIdx.x; i < n; i += T) {
-      float2 p = pts[i];
+      const float2 p = (i == (int)threadIdx.x) ? p_first : pts[i];
       HsBeam b = hs_make_beam(L, bx, by, mpx, mpy, sn, cs, p.x * pf, p.y * pf);
       HsBeamRec r;
       r.kend = b.kend; r.da = 0; r.db = (unsigned short)b.abs_db;
@@ -1195,6 +1204,7 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS, 3) k_raycast(HsParams P, i
       w.seg_start = (int)(unsigned)(base & 0xFFFFFFFFULL) + incl - nseg;
       const int pos = (int)(base >> 32) + __popc(m & ((1u << lane) - 1u));
       walk[pos] = w;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(val + r.kend));   // phase C reads this cell: have it in L2 by then
       if (single_band) {   // the whole trace lies in the one band; mark the end cell in the (already cleared) map
         tlo[pos] = 0;
         tlen[pos] = r.da;
@@ -1385,7 +1395,7 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS, 3) k_raycast(HsParams P, i
             if (bits[u] & 4u) w.z = w.z + f;
             if (bits[u] & 8u) w.w = w.w + f;
             *reinterpret_cast<float4*>(val + g[u]) = w;
-            if (bits[u] == 0xFu) {
+            if (bits[u] == 0xFu || (P.dbg_skip & 64)) {   // bit 6 (timing experiment, wrong markers): every quad as one 16-byte store
               *reinterpret_cast<int4*>(idx + g[u]) = mf4;
             } else {
               if (bits[u] & 1u) idx[g[u]] = mark_free;
