@@ -186,6 +186,7 @@ def main():
         raise SystemExit("bench.py --impl ours needs a CUDA device: hsgpu has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries exactly one JSON line (NCCL's version banner goes to stderr)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     steps = W + K

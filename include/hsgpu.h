@@ -126,6 +126,20 @@ int hs_scan_to_points_host_batch(const float* ranges, int n_scans, int n_beams, 
                                  float range_min, float range_max, float scale_to_map, int max_points,
                                  float* points_out, int32_t* counts_out, int threads);
 
+/* The node's default ingestion path (use_tf_scan_transformation, HectorMappingRos.cpp:273-282):
+ * rosPointCloudToDataContainer (HectorMappingRos.cpp:509-542) for n clouds on the GPU, then update(). clouds_xyz
+ * [n][max_cloud][3] laser-frame points, cloud_counts [n]; transforms12 [n][12] = the laser->base tf::Transform as
+ * row-major 3x3 basis followed by the origin, in double like tf; filters = the node's parameters
+ * (laser_min_dist^2, laser_max_dist^2, laser_z_min_value, laser_z_max_value, :98-108). origo = laser position * scaleToMap.
+ * Points beyond max_points are dropped. Host pointers. */
+int hs_update_batch_clouds(hs_engine* e, int n, const int32_t* stream_ids, const float* clouds_xyz, const int32_t* cloud_counts,
+                           int max_cloud, const double* transforms12, float sqr_min_dist, float sqr_max_dist, float z_min, float z_max,
+                           const float* pose_hints, const uint8_t* map_without_matching, float* poses_out, float* cov_out);
+/* Host helper with the same arithmetic for one cloud (callers that want DataContainer points + origo). Returns the count. */
+int hs_cloud_to_points_host(const float* cloud_xyz, int n_cloud, const double* transform12, float scale_to_map,
+                            float sqr_min_dist, float sqr_max_dist, float z_min, float z_max, int max_points,
+                            float* points_out, float* origo_out);
+
 /* getLastScanMatchPose / getLastScanMatchCovariance (HectorSlamProcessor.h:126-127) of streams
  * [first, first+n) into host memory. hs_get_last_map_update_poses exposes lastMapUpdatePose. */
 int hs_get_poses(hs_engine* e, int first, int n, float* poses_out);

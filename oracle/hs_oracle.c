@@ -633,6 +633,40 @@ int hso_scan_to_points(const float* ranges, int n_beams, float angle_min, float 
 
 /* ------------------------------------------------------------- stream runner ---- */
 
+/* HectorMappingRos::rosPointCloudToDataContainer (src/hector_slam/hector_mapping/src/HectorMappingRos.cpp:509-542).
+ * tf is a ROS dependency absent from /root/reference and from this image (PARITY UNPINNED for its arithmetic): restated
+ * from tf/LinearMath/Transform.h / Vector3.h / Matrix3x3.h (tfScalar = double): Transform * v = Vector3(basis[0].dot(v) +
+ * origin.x, basis[1].dot(v) + origin.y, basis[2].dot(v) + origin.z), dot = x*x' + y*y' + z*z' evaluated left to right.
+ * transform12 = row-major basis, then origin. Returns the number of points written (x,y interleaved), origo_out = laser
+ * position * scaleToMap. */
+int hso_cloud_to_points(const float* cloud_xyz, int n_cloud, const double* transform12, float scale_to_map,
+                        float sqr_min_dist, float sqr_max_dist, float z_min, float z_max, float* pts_out, float* origo_out) {
+  const double* b = transform12;
+  const double* o = transform12 + 9;
+  origo_out[0] = (float)o[0] * scale_to_map;
+  origo_out[1] = (float)o[1] * scale_to_map;
+  int count = 0;
+  for (int i = 0; i < n_cloud; ++i) {
+    float cx = cloud_xyz[3 * i], cy = cloud_xyz[3 * i + 1], cz = cloud_xyz[3 * i + 2];
+    float dist_sqr = cx * cx + cy * cy;
+    if ((dist_sqr > sqr_min_dist) && (dist_sqr < sqr_max_dist)) {
+      if ((cx < 0.0f) && (dist_sqr < 0.50f)) continue;
+      double vx = cx, vy = cy, vz = cz;
+      double px = (b[0] * vx + b[1] * vy + b[2] * vz) + o[0];
+      double py = (b[3] * vx + b[4] * vy + b[5] * vz) + o[1];
+      double pz = (b[6] * vx + b[7] * vy + b[8] * vz) + o[2];
+      float z_laser = (float)(pz - o[2]);
+      if (z_laser > z_min && z_laser < z_max) {
+        pts_out[2 * count] = (float)px * scale_to_map;
+        pts_out[2 * count + 1] = (float)py * scale_to_map;
+        ++count;
+      }
+    }
+  }
+  return count;
+}
+
+
 typedef struct {
   hso_proc** procs; int n_streams, n_scans, max_pts; const float* pts; const int* counts;
   int threads, tid, stream_major; float* poses_out; float* cov_out;

@@ -72,6 +72,11 @@ unsigned long long hso_get_integrations(hso_proc* p);
 int hso_scan_to_points(const float* ranges, int n_beams, float angle_min, float angle_increment,
                        float range_min, float range_max, float scale_to_map, float* pts_out);
 
+/* rosPointCloudToDataContainer (HectorMappingRos.cpp:509-542); transform12 = row-major 3x3 basis + origin of the
+ * laser->base tf::Transform (double). Returns the number of points written; origo_out[2] = laser position * scaleToMap. */
+int hso_cloud_to_points(const float* cloud_xyz, int n_cloud, const double* transform12, float scale_to_map,
+                        float sqr_min_dist, float sqr_max_dist, float z_min, float z_max, float* pts_out, float* origo_out);
+
 /* Multi-stream CPU runner, same contract as hsref_run_streams in ref_driver.cpp. */
 double hso_run_streams(hso_proc** procs, int n_streams, int n_scans, int max_pts, const float* pts, const int* counts,
                        int threads, int stream_major, float* poses_out, float* cov_out);

@@ -74,6 +74,7 @@ def _load(kind):
         sig["get_cell_visits"] = (ctypes.c_ulonglong, [_P])
         sig["get_integrations"] = (ctypes.c_ulonglong, [_P])
         sig["scan_to_points"] = (_I, [_P, _I, _F, _F, _F, _F, _F, _P])
+        sig["cloud_to_points"] = (_I, [_P, _I, _P, _F, _F, _F, _F, _F, _P, _P])
     fns = {}
     for name, (res, args) in sig.items():
         fn = getattr(L, pre + name)
@@ -218,6 +219,17 @@ class CpuProcessor:
 
     def cell_visits(self): return int(self.f["get_cell_visits"](self.h))
     def integrations(self): return int(self.f["get_integrations"](self.h))
+
+
+def cloud_to_points(cloud_xyz, transform12, scale_to_map, sqr_min_dist, sqr_max_dist, z_min, z_max):
+    """rosPointCloudToDataContainer (C restatement only: the node needs ROS/tf): (points [k][2], origo [2])."""
+    cloud_xyz = _f32(cloud_xyz).reshape(-1, 3)
+    t = np.ascontiguousarray(transform12, np.float64).reshape(12)
+    pts = np.zeros((max(cloud_xyz.shape[0], 1), 2), np.float32)
+    origo = np.zeros(2, np.float32)
+    k = _load("port")["cloud_to_points"](cloud_xyz.ctypes.data, cloud_xyz.shape[0], t.ctypes.data, scale_to_map, sqr_min_dist,
+                                         sqr_max_dist, z_min, z_max, pts.ctypes.data, origo.ctypes.data)
+    return pts[:k].copy(), origo
 
 
 def check_occupancy_bresenhami(kind, grid, begin, end):

@@ -342,3 +342,35 @@ def test_pinned_host_batches_are_chunked_and_identical(hs, monkeypatch):
         assert np.array_equal(bits(poses), bits(base[2])), (chunks, use_ids)     # slot i always carries scan stream i's points
         for a, b in zip(maps, base[4]):
             assert np.array_equal(bits(a), bits(b)), (chunks, use_ids)
+
+
+def test_point_cloud_entry_point_equals_oracle_pipeline(hs, oracle):
+    """hs_update_batch_clouds = rosPointCloudToDataContainer on the GPU + update(): against the oracle's cloud conversion
+    followed by the CPU processor (points AND offset origo), bit for bit, ragged clouds incl. an empty one."""
+    from test_scangen import _laser_transform
+    rng = np.random.default_rng(31)
+    n, n_scans, max_cloud = 5, 8, 400
+    sc, ranges, pts, cnt, truth = make_streams(hs, n, n_scans, seed0=606)
+    eng, procs = setup_pair(hs, oracle, n, max_points=360)
+    filt = (np.float32(0.16), np.float32(900.0), np.float32(-1.0), np.float32(1.0))
+    for k in range(n_scans):
+        clouds = np.zeros((n, max_cloud, 3), np.float32)
+        counts = np.zeros(n, np.int32)
+        xf = np.zeros((n, 12), np.float64)
+        for s in range(n):
+            m = int(cnt[k, s]) if not (k == 3 and s == 2) else 0
+            # laser-frame cloud in metres from the synthetic scan points (cells / 20), plus a z spread that the z window cuts
+            clouds[s, :m, :2] = pts[k, s, :m] / np.float32(20.0)
+            clouds[s, :m, 2] = rng.uniform(-1.2, 1.2, m).astype(np.float32)
+            counts[s] = m
+            t = _laser_transform(rng); t[:9] = np.eye(3).reshape(-1); t[9:] = (0.1 * s, -0.05 * s, 0.3)   # pure offset mount
+            xf[s] = t
+        out, cov = eng.update_batch_clouds(clouds, counts, xf, *filt)
+        for s, p in enumerate(procs):
+            cp, co = oracle.cloud_to_points(clouds[s, :counts[s]], xf[s], np.float32(20.0), *filt)
+            ref = p.update(cp, len(cp), origo=co, hint=p.pose())
+            assert np.array_equal(bits(out[s]), bits(ref)), (k, s)
+    assert_same_maps(eng, procs, 3)
+    eng.close()
+    for p in procs:
+        p.close()

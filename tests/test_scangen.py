@@ -42,3 +42,31 @@ def test_scan_to_points_matches_oracle_restatement(hs, oracle):
         assert cnt[i] == ref.shape[0]
         assert np.array_equal(bits(pts[i, :cnt[i]]), bits(ref))
     assert cnt[2] == 0 and cnt[3] == 0 and cnt[0] < 360
+
+
+def _laser_transform(rng):
+    """A laser->base tf::Transform: yaw + small roll/pitch, offset origin; row-major basis then origin (double)."""
+    yaw, pitch, roll = rng.uniform(-3, 3), rng.uniform(-0.05, 0.05), rng.uniform(-0.05, 0.05)
+    cy, sy, cp, sp, cr, sr = np.cos(yaw), np.sin(yaw), np.cos(pitch), np.sin(pitch), np.cos(roll), np.sin(roll)
+    R = np.array([[cy * cp, cy * sp * sr - sy * cr, cy * sp * cr + sy * sr],
+                  [sy * cp, sy * sp * sr + cy * cr, sy * sp * cr - cy * sr],
+                  [-sp, cp * sr, cp * cr]])
+    return np.concatenate([R.reshape(-1), rng.uniform(-0.3, 0.3, 3)])
+
+
+def test_cloud_to_points_host_matches_oracle(hs, oracle):
+    """rosPointCloudToDataContainer (HectorMappingRos.cpp:509-542): the product's host helper against the oracle's C
+    restatement, bit for bit -- distance window, rear-point rejection, z window, origo, empty cloud."""
+    rng = np.random.default_rng(12)
+    for trial in range(20):
+        n = int(rng.integers(0, 500))
+        cloud = np.concatenate([rng.uniform(-6, 6, (n, 2)), rng.uniform(-1.5, 1.5, (n, 1))], 1).astype(np.float32)
+        if n > 10:
+            cloud[:5] = [(-0.5, 0.2, 0), (0.5, 0.2, 0), (0.39, 0.0, 0), (0.0, 0.41, 0), (-0.7, 0.1, 0.0)]
+        t = _laser_transform(rng)
+        args = (np.float32(20.0), np.float32(0.4 * 0.4), np.float32(30.0 * 30.0) if trial % 2 else np.float32(25.0), np.float32(-1.0), np.float32(1.0))
+        a, oa = hs.cloud_to_points_host(cloud, t, *args)
+        b, ob = oracle.cloud_to_points(cloud, t, *args)
+        assert a.shape == b.shape and np.array_equal(a.view(np.int32), b.view(np.int32)) and np.array_equal(oa.view(np.int32), ob.view(np.int32))
+        if n > 10:
+            assert len(a) < n   # some points were filtered

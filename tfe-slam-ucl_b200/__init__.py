@@ -123,6 +123,8 @@ def lib():
         "hs_download_level": (_I, [_P, _I, _I, _P]), "hs_upload_level": (_I, [_P, _I, _I, _P]),
         "hs_get_update_index": (_I, [_P, _I, _I, _P]), "hs_classify_level": (_I, [_P, _I, _I, _P]),
         "hs_get_stats": (_I, [_P, _P]), "hs_get_map_info": (_I, [_P, _I, _P]),
+        "hs_update_batch_clouds": (_I, [_P, _I, _P, _P, _P, _I, _P, _F, _F, _F, _F, _P, _P, _P, _P]),
+        "hs_cloud_to_points_host": (_I, [_P, _I, _P, _F, _F, _F, _F, _F, _I, _P, _P]),
         "hs_likelihood_batch": (_I, [_P, _I, _I, _P, _I, _P, _I, _P, _P]),
         "hs_covariance_for_pose": (_I, [_P, _I, _I, _P, _P, _I, _P, _P]),
         "hs_interp_map_value_batch": (_I, [_P, _I, _I, _P, _I, _P, _P]),
@@ -193,6 +195,20 @@ def scan_to_points_host(ranges, scene, scale_to_map, max_points=None):
                                               scene.range_min, scene.range_max, scale_to_map, mp, pts.ctypes.data,
                                               cnt.ctypes.data, os.cpu_count() or 1), "hs_scan_to_points_host_batch")
     return pts.reshape(lead + (mp, 2)), cnt.reshape(lead)
+
+
+def cloud_to_points_host(cloud_xyz, transform12, scale_to_map, sqr_min_dist, sqr_max_dist, z_min, z_max, max_points=None):
+    """rosPointCloudToDataContainer for one cloud on the host -> (points [k][2], origo [2])."""
+    cloud_xyz = np.ascontiguousarray(cloud_xyz, np.float32).reshape(-1, 3)
+    t = np.ascontiguousarray(transform12, np.float64).reshape(12)
+    mp = max_points or max(cloud_xyz.shape[0], 1)
+    pts = np.zeros((mp, 2), np.float32)
+    origo = np.zeros(2, np.float32)
+    k = lib().hs_cloud_to_points_host(cloud_xyz.ctypes.data, cloud_xyz.shape[0], t.ctypes.data, scale_to_map, sqr_min_dist,
+                                      sqr_max_dist, z_min, z_max, mp, pts.ctypes.data, origo.ctypes.data)
+    if k < 0:
+        raise HsError(k, "hs_cloud_to_points_host")
+    return pts[:k].copy(), origo
 
 
 # ---- the engine ------------------------------------------------------------------------------------
@@ -282,6 +298,23 @@ class Engine:
         cov = np.empty((n, 9), np.float32) if want_cov else None
         _check(lib().hs_update_batch_ranges(self._h, n, _ptr(ids), ranges.ctypes.data, _ptr(pose_hints), _ptr(flags),
                                             poses.ctypes.data, _ptr(cov)), "hs_update_batch_ranges")
+        return poses, (cov.reshape(n, 3, 3) if want_cov else None)
+
+    def update_batch_clouds(self, clouds_xyz, cloud_counts, transforms12, sqr_min_dist, sqr_max_dist, z_min, z_max,
+                            pose_hints=None, map_without_matching=None, stream_ids=None, want_cov=True):
+        """rosPointCloudToDataContainer on the GPU + update(): clouds_xyz [n][max_cloud][3], transforms12 [n][12] (double)."""
+        cloud_counts = _arr(cloud_counts, np.int32)
+        n = cloud_counts.shape[0]
+        clouds_xyz = np.ascontiguousarray(clouds_xyz, np.float32).reshape(n, -1, 3)
+        transforms12 = np.ascontiguousarray(transforms12, np.float64).reshape(n, 12)
+        pose_hints = _arr(pose_hints, np.float32, (n, 3))
+        flags = _arr(map_without_matching, np.uint8, (n,))
+        ids = _arr(stream_ids, np.int32, (n,))
+        poses = np.empty((n, 3), np.float32)
+        cov = np.empty((n, 9), np.float32) if want_cov else None
+        _check(lib().hs_update_batch_clouds(self._h, n, _ptr(ids), clouds_xyz.ctypes.data, cloud_counts.ctypes.data, clouds_xyz.shape[1],
+                                            transforms12.ctypes.data, sqr_min_dist, sqr_max_dist, z_min, z_max, _ptr(pose_hints),
+                                            _ptr(flags), poses.ctypes.data, _ptr(cov)), "hs_update_batch_clouds")
         return poses, (cov.reshape(n, 3, 3) if want_cov else None)
 
     def update_batch_ranges_raw(self, n, ranges_ptr, poses_out_ptr, hints_ptr=None, flags_ptr=None, ids_ptr=None, cov_out_ptr=None):

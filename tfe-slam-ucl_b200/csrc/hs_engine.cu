@@ -683,6 +683,65 @@ int hs_update_batch_ranges(hs_engine* e, int n, const int32_t* stream_ids, const
   return HS_OK;
 }
 
+// ---- point-cloud ingestion (the node's default path, HectorMappingRos.cpp:273-282, :509-542) -------------------
+
+int hs_cloud_to_points_host(const float* cloud_xyz, int n_cloud, const double* transform12, float scale_to_map,
+                            float sqr_min_dist, float sqr_max_dist, float z_min, float z_max, int max_points,
+                            float* points_out, float* origo_out) {
+  if (n_cloud < 0 || (!cloud_xyz && n_cloud > 0) || !transform12 || !points_out || max_points < 0) return HS_ERR_INVALID_ARG;
+  const HsCloudFilter F = {sqr_min_dist, sqr_max_dist, z_min, z_max};
+  int count = 0;
+  for (int i = 0; i < n_cloud; ++i) {
+    float px, py;
+    if (hs_cloud_point(cloud_xyz + 3 * (size_t)i, transform12, F, scale_to_map, px, py)) {
+      if (count < max_points) { points_out[2 * count] = px; points_out[2 * count + 1] = py; }
+      ++count;
+    }
+  }
+  if (origo_out) { origo_out[0] = (float)transform12[9] * scale_to_map; origo_out[1] = (float)transform12[10] * scale_to_map; }
+  return count < max_points ? count : max_points;
+}
+
+int hs_update_batch_clouds(hs_engine* e, int n, const int32_t* stream_ids, const float* clouds_xyz, const int32_t* cloud_counts,
+                           int max_cloud, const double* transforms12, float sqr_min_dist, float sqr_max_dist, float z_min, float z_max,
+                           const float* pose_hints, const uint8_t* map_without_matching, float* poses_out, float* cov_out) {
+  int st = check_batch(e, n);
+  if (st != HS_OK) return st;
+  if (n == 0) return HS_OK;
+  if (!clouds_xyz || !cloud_counts || !transforms12 || max_cloud < 1) return HS_ERR_INVALID_ARG;
+  if ((st = check_ids(e, n, stream_ids)) != HS_OK) return st;
+  HS_CK(cudaSetDevice(e->device));
+  auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t b_c = (size_t)n * max_cloud * 3 * sizeof(float), b_n = (size_t)n * sizeof(int32_t), b_t = (size_t)n * 12 * sizeof(double);
+  const size_t o_n = align(b_c), o_t = o_n + align(b_n);
+  if ((st = ensure_scratch(e, o_t + b_t)) != HS_OK) return st;
+  char* base = (char*)e->d_scratch;
+  HS_CK(cudaMemcpyAsync(base, clouds_xyz, b_c, cudaMemcpyHostToDevice, e->stream));
+  HS_CK(cudaMemcpyAsync(base + o_n, cloud_counts, b_n, cudaMemcpyHostToDevice, e->stream));
+  HS_CK(cudaMemcpyAsync(base + o_t, transforms12, b_t, cudaMemcpyHostToDevice, e->stream));
+  e->h2d_bytes += b_c + b_n + b_t;
+  if ((st = stage_common(e, n, stream_ids, nullptr, nullptr, pose_hints, map_without_matching)) != HS_OK) return st;
+  const HsCloudFilter F = {sqr_min_dist, sqr_max_dist, z_min, z_max};
+  {
+    ProfScope ps(e, HS_K_SCAN_TO_POINTS);
+    k_cloud_to_points<<<warp_grid(n, 128), 128, 0, e->stream>>>((const float*)base, (const int32_t*)(base + o_n), n, max_cloud,
+                                                                (const double*)(base + o_t), F, e->P.lv[0].scale, e->P.max_points,
+                                                                (float2*)e->d_points, e->d_counts, (float2*)e->d_origos);
+  }
+  HS_LAUNCHED(e);
+  const int32_t* d_ids = stream_ids ? e->d_ids : nullptr;
+  st = run_update_device(e, n, d_ids, e->d_points, e->d_counts, e->d_origos, pose_hints ? e->d_hints : nullptr,
+                         map_without_matching ? e->d_flags : nullptr, 0);
+  if (st != HS_OK) return st;
+  if ((st = fetch_rows(e, e->P.last_pose, d_ids, 0, n, 3, poses_out)) != HS_OK) return st;
+  if (cov_out) {
+    if (stream_ids && poses_out) HS_CK(cudaStreamSynchronize(e->stream));
+    if ((st = fetch_rows(e, e->P.cov, d_ids, 0, n, 9, cov_out)) != HS_OK) return st;
+  }
+  HS_CK(cudaStreamSynchronize(e->stream));
+  return HS_OK;
+}
+
 static int get_rows(hs_engine* e, const float* d_src, int first, int n, int width, float* out) {
   if (!e || !out || first < 0 || n < 0 || first + n > e->P.n_streams) return HS_ERR_INVALID_ARG;
   HS_CK(cudaSetDevice(e->device));

@@ -143,6 +143,62 @@ __global__ void __launch_bounds__(128) k_scan_to_points(const float* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_cloud_to_points: HectorMappingRos::rosPointCloudToDataContainer (HectorMappingRos.cpp:509-542), the node's default
+// ingestion path (use_tf_scan_transformation): laser-frame points (x, y, z) -> DataContainer points in the base frame,
+// scaled to level-0 cells, with the reference's filters (squared planar distance window, rear points closer than
+// sqrt(0.5) m dropped, z window in the laser frame) and origo = laser position * scaleToMap. tf (absent here) works in
+// double: T * v = (basis.row(i) . v) + origin_i, products summed left to right (tf/LinearMath/Transform.h, Vector3.h).
+// One warp per cloud; xf [n][12] = row-major 3x3 basis then origin. Ordered compaction like the reference's push_back.
+struct HsCloudFilter { float sqr_min_dist, sqr_max_dist, z_min, z_max; };
+
+__host__ __device__ __forceinline__ bool hs_cloud_point(const float* p3, const double* xf, const HsCloudFilter& F, float scale_to_map,
+                                                        float& ox, float& oy) {
+  const float x = p3[0], y = p3[1], z = p3[2];
+  const float dist_sqr = x * x + y * y;
+  if (!((dist_sqr > F.sqr_min_dist) && (dist_sqr < F.sqr_max_dist))) return false;
+  if ((x < 0.0f) && (dist_sqr < 0.50f)) return false;
+  const double vx = (double)x, vy = (double)y, vz = (double)z;
+  const double bx = ((xf[0] * vx + xf[1] * vy) + xf[2] * vz) + xf[9];
+  const double by = ((xf[3] * vx + xf[4] * vy) + xf[5] * vz) + xf[10];
+  const double bz = ((xf[6] * vx + xf[7] * vy) + xf[8] * vz) + xf[11];
+  const float z_laser = (float)(bz - xf[11]);
+  if (!(z_laser > F.z_min && z_laser < F.z_max)) return false;
+  ox = (float)bx * scale_to_map;
+  oy = (float)by * scale_to_map;
+  return true;
+}
+
+__global__ void __launch_bounds__(128) k_cloud_to_points(const float* __restrict__ clouds, const int32_t* __restrict__ cloud_counts, int n_slots,
+                                                         int max_cloud, const double* __restrict__ xf, HsCloudFilter F, float scale_to_map,
+                                                         int max_points, float2* __restrict__ points, int* __restrict__ counts,
+                                                         float2* __restrict__ origos) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= n_slots) return;
+  const float* c = clouds + (size_t)warp * max_cloud * 3;
+  const double* t = xf + (size_t)warp * 12;
+  float2* out = points + (size_t)warp * max_points;
+  int n = cloud_counts[warp];
+  n = n < 0 ? 0 : (n > max_cloud ? max_cloud : n);
+  int base = 0;
+  for (int i0 = 0; i0 < n; i0 += 32) {
+    const int i = i0 + lane;
+    float px = 0.0f, py = 0.0f;
+    const bool valid = (i < n) && hs_cloud_point(c + 3 * (size_t)i, t, F, scale_to_map, px, py);
+    const unsigned m = __ballot_sync(0xffffffffu, valid);
+    if (valid) {
+      const int pos = base + __popc(m & ((1u << lane) - 1u));
+      if (pos < max_points) out[pos] = make_float2(px, py);
+    }
+    base += __popc(m);
+  }
+  if (lane == 0) {
+    counts[warp] = base < max_points ? base : max_points;
+    origos[warp] = make_float2((float)t[9] * scale_to_map, (float)t[10] * scale_to_map);   // Vector2f(laserPos.x(), laserPos.y()) * scaleToMap
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Matching: OccGridMapUtil::getCompleteHessianDerivs + interpMapValueWithDerivatives
 // (HSL/map/OccGridMapUtil.h:64-104, :287-347).
 
