@@ -45,7 +45,7 @@ struct hs_engine {
   // bookkeeping
   uint64_t updates, launches, h2d_bytes, d2h_bytes;
   float free_factor, occ_factor;
-  int match_v2;              // matcher variant: k_match2 (shared-memory cache, dense probability pass) for long scans, k_match
+  int match_variant;         // matcher variant: 2 = k_match2 (shared-memory cache, dense probability pass) for long scans, k_match
                              // (register cache) for scans of <= 768 points; HSGPU_MATCH_VARIANT=1|2 overrides
   int log2_seg_levels;       // k_raycast walk segment lengths (log2): level 0 | coarser levels << 8
   // optional per-kernel timing with CUDA events on the launching stream (hs_profile_*)
@@ -216,11 +216,11 @@ int hs_create(const hs_config* cfg, hs_engine** out) {
   }
   P.cells_per_stream = off;
   {
-    int s0 = 5, s1 = 4;   // 32-step segments on the fine grid, 16-step segments on the coarse ones
+    int s0 = 4, s1 = 2;   // 16-step segments on the fine grid, 4-step segments on the coarse ones (measured on B200: 5,4 217 us; 4,2 214; 0,0 224)
     const char* env = getenv("HSGPU_RAYCAST_SEG_LOG2");   // tuning hook: "<level0>,<coarse>"
     if (env) sscanf(env, "%d,%d", &s0, &s1);
-    s0 = s0 < 2 ? 2 : (s0 > 12 ? 12 : s0);
-    s1 = s1 < 2 ? 2 : (s1 > 12 ? 12 : s1);
+    s0 = s0 < 0 ? 0 : (s0 > 12 ? 12 : s0);
+    s1 = s1 < 0 ? 0 : (s1 > 12 ? 12 : s1);
     e->log2_seg_levels = s0 | (s1 << 8);
   }
   e->free_factor = 0.4f;
@@ -295,8 +295,12 @@ int hs_create(const hs_config* cfg, hs_engine** out) {
         return (int)(e1 != cudaSuccess ? e1 : e2);
       }
     }
-    e->match_v2 = cfg->max_points > 768;   // measured on B200: 360 points: k_match 92 us vs k_match2 127 us per 1024 scans; 1440 points: 400 vs 353
-    if (const char* mv = getenv("HSGPU_MATCH_VARIANT")) e->match_v2 = atoi(mv) == 2;
+    // measured on B200: 360 points: k_match 92 us vs k_match2 127 us per 1024 scans; 1440 points: 400 vs 353
+    e->match_variant = cfg->max_points > 768 ? 2 : 1;
+    if (const char* mv = getenv("HSGPU_MATCH_VARIANT")) {
+      const int v = atoi(mv);
+      if (v == 1 || v == 2) e->match_variant = v;
+    }
     int smem2 = (int)match2_smem_for(cfg->max_points);
     if (smem2 > 48 * 1024) {
       cudaError_t e4 = cudaFuncSetAttribute(k_match2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
@@ -468,7 +472,7 @@ static int run_update_device(hs_engine* e, int n, const int32_t* ids, const floa
   {
     ProfScope ps(e, HS_K_MATCH);
     const int threads = HS_MATCH_THREADS;
-    if (e->match_v2) {
+    if (e->match_variant == 2) {
       const size_t smem2 = match2_smem_for(e->P.max_points);
       if (e->P.strict)
         k_match2<true><<<n, threads, smem2, st>>>(Pc, n, ids, (const float2*)points, counts, (const float2*)origos, hints, flags, mode);
