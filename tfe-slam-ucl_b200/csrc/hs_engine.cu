@@ -286,7 +286,7 @@ int hs_create(const hs_config* cfg, hs_engine** out) {
     }
   }
   {
-    int smem = cfg->max_points * HS_NPROD * (int)sizeof(float);  // k_match's per-CTA product buffer
+    int smem = hs_match2_pitch(cfg->max_points) * HS_NPROD * (int)sizeof(float);  // k_match's per-CTA product buffer
     if (smem > 48 * 1024) {
       cudaError_t e1 = cudaFuncSetAttribute(k_match<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
       cudaError_t e2 = cudaFuncSetAttribute(k_match<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -479,7 +479,7 @@ static int run_update_device(hs_engine* e, int n, const int32_t* ids, const floa
       else
         k_match2<false><<<n, threads, smem2, st>>>(Pc, n, ids, (const float2*)points, counts, (const float2*)origos, hints, flags, mode);
     } else {
-    const size_t smem = (size_t)e->P.max_points * HS_NPROD * sizeof(float);
+    const size_t smem = (size_t)hs_match2_pitch(e->P.max_points) * HS_NPROD * sizeof(float);
     int ppt = (e->P.max_points + threads - 1) / threads;   // register-resident points (+ cell caches) per thread
     ppt = ppt <= 2 ? 2 : (ppt <= 3 ? 3 : (ppt <= 6 ? 6 : 0));
 #define HS_LAUNCH_MATCH(STRICT_, PPT_)                                                               \
@@ -780,7 +780,7 @@ int hs_hessian_derivs_batch(hs_engine* e, int stream, int level, const float* po
   HS_CK(cudaMemcpyAsync(base, poses_map, b_poses, cudaMemcpyHostToDevice, e->stream));
   if (n_points > 0) HS_CK(cudaMemcpyAsync(base + o_pts, points, (size_t)n_points * 2 * sizeof(float), cudaMemcpyHostToDevice, e->stream));
   e->h2d_bytes += b_poses + (size_t)n_points * 8;
-  const size_t smem = (size_t)(n_points > 0 ? n_points : 1) * HS_NPROD * sizeof(float);
+  const size_t smem = (size_t)hs_match2_pitch(n_points > 0 ? n_points : 1) * HS_NPROD * sizeof(float);
   if (smem > 200 * 1024) return HS_ERR_INVALID_ARG;
   if (smem > 48 * 1024) {
     HS_CK(cudaFuncSetAttribute(k_hessian_derivs<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

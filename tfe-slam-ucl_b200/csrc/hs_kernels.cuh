@@ -289,16 +289,22 @@ struct HsMatchTimer {
 // Must be called by all threads of the CTA; contains two __syncthreads. Only the serial warp's return value is defined.
 #define HS_NPROD 9
 
-__device__ __forceinline__ void hs_store_products(float* __restrict__ q, float gx, float gy, float rot, float fv) {
-  q[0] = gx * fv;   // dTr[0]
-  q[1] = gy * fv;   // dTr[1]
-  q[2] = rot * fv;  // dTr[2]
-  q[3] = gx * gx;   // H(0,0)
-  q[4] = gy * gy;   // H(1,1)
-  q[5] = rot * rot; // H(2,2)
-  q[6] = gx * gy;   // H(0,1)
-  q[7] = gx * rot;  // H(0,2)
-  q[8] = gy * rot;  // H(1,2)
+// Products are stored SUM-MAJOR: prod[k * pitch + i] = k-th product of point i, so that the lane that owns sum k reads
+// four consecutive terms of its chain per 16-byte shared load; pitch == 4 (mod 32) keeps those reads conflict-free.
+__host__ __device__ __forceinline__ int hs_match2_pitch(int max_points) {   // >= max_points, == 4 (mod 32)
+  return ((max_points + 27) & ~31) + 4;
+}
+
+__device__ __forceinline__ void hs_store_products(float* __restrict__ q, int pitch, float gx, float gy, float rot, float fv) {
+  q[0] = gx * fv;             // dTr[0]
+  q[pitch] = gy * fv;         // dTr[1]
+  q[2 * pitch] = rot * fv;    // dTr[2]
+  q[3 * pitch] = gx * gx;     // H(0,0)
+  q[4 * pitch] = gy * gy;     // H(1,1)
+  q[5 * pitch] = rot * rot;   // H(2,2)
+  q[6 * pitch] = gx * gy;     // H(0,1)
+  q[7 * pitch] = gx * rot;    // H(0,2)
+  q[8 * pitch] = gy * rot;    // H(1,2)
 }
 
 // PPT > 0: the thread's points (i = tid + j*blockDim, j < PPT) are held in registers by the caller (they are the
@@ -306,7 +312,7 @@ __device__ __forceinline__ void hs_store_products(float* __restrict__ q, float g
 template <bool STRICT, int PPT>
 __device__ __forceinline__ HsAcc hs_eval_cta(const float* __restrict__ val, const HsLevel& L, float ex, float ey, float sn, float cs,
                                              const float2* __restrict__ pts, const float2* preg, HsCellCache* cache, int n,
-                                             float pt_factor, float* __restrict__ prod, int serial_warp = 0, HsMatchTimer* mt = nullptr) {
+                                             float pt_factor, float* __restrict__ prod, int pitch, int serial_warp = 0, HsMatchTimer* mt = nullptr) {
   if (PPT > 0) {
 #pragma unroll
     for (int j = 0; j < (PPT > 0 ? PPT : 1); ++j) {
@@ -314,7 +320,7 @@ __device__ __forceinline__ HsAcc hs_eval_cta(const float* __restrict__ val, cons
       if (i < n) {
         float gx, gy, rot, fv;
         hs_point_terms<true>(val, L, ex, ey, sn, cs, preg[j].x * pt_factor, preg[j].y * pt_factor, cache[j], gx, gy, rot, fv);
-        hs_store_products(prod + i * HS_NPROD, gx, gy, rot, fv);
+        hs_store_products(prod + i, pitch, gx, gy, rot, fv);
       }
     }
   } else {
@@ -323,7 +329,7 @@ __device__ __forceinline__ HsAcc hs_eval_cta(const float* __restrict__ val, cons
       float gx, gy, rot, fv;
       HsCellCache none;
       hs_point_terms<false>(val, L, ex, ey, sn, cs, p.x * pt_factor, p.y * pt_factor, none, gx, gy, rot, fv);
-      hs_store_products(prod + i * HS_NPROD, gx, gy, rot, fv);
+      hs_store_products(prod + i, pitch, gx, gy, rot, fv);
     }
   }
   __syncthreads();
@@ -334,14 +340,14 @@ __device__ __forceinline__ HsAcc hs_eval_cta(const float* __restrict__ val, cons
     float acc = 0.0f;
     if (STRICT) {
       if (lane < HS_NPROD) {
-        const float* q = prod + lane;
-        int i = 0;
-        for (; i + 8 <= n; i += 8) {  // loads are independent of the chain and issue ahead of it
-          float t0 = q[(i + 0) * HS_NPROD], t1 = q[(i + 1) * HS_NPROD], t2 = q[(i + 2) * HS_NPROD], t3 = q[(i + 3) * HS_NPROD];
-          float t4 = q[(i + 4) * HS_NPROD], t5 = q[(i + 5) * HS_NPROD], t6 = q[(i + 6) * HS_NPROD], t7 = q[(i + 7) * HS_NPROD];
-          acc += t0; acc += t1; acc += t2; acc += t3; acc += t4; acc += t5; acc += t6; acc += t7;
+        const float* q = prod + lane * pitch;
+        const float4* q4 = reinterpret_cast<const float4*>(q);
+        const int n4 = n >> 2;
+        for (int i = 0; i < n4; ++i) {  // loads are independent of the chain and issue ahead of it
+          const float4 t = q4[i];
+          acc += t.x; acc += t.y; acc += t.z; acc += t.w;
         }
-        for (; i < n; ++i) acc += q[i * HS_NPROD];
+        for (int i = n4 << 2; i < n; ++i) acc += q[i];
       }
       a.d0 = __shfl_sync(0xffffffffu, acc, 0);
       a.d1 = __shfl_sync(0xffffffffu, acc, 1);
@@ -358,7 +364,7 @@ __device__ __forceinline__ HsAcc hs_eval_cta(const float* __restrict__ val, cons
       for (int k = 0; k < HS_NPROD; ++k) r[k] = 0.0f;
       for (int i = lane; i < n; i += 32) {
 #pragma unroll
-        for (int k = 0; k < HS_NPROD; ++k) r[k] += prod[i * HS_NPROD + k];
+        for (int k = 0; k < HS_NPROD; ++k) r[k] += prod[k * pitch + i];
       }
 #pragma unroll
       for (int m = 16; m >= 1; m >>= 1) {
@@ -446,7 +452,7 @@ __global__ void __launch_bounds__(HS_MATCH_THREADS, (PPT > 0 && PPT <= 3) ? 7 : 
                                                             const float2* __restrict__ points, const int32_t* __restrict__ counts,
                                                             const float2* __restrict__ origos, const float* __restrict__ hints,
                                                             const uint8_t* __restrict__ mwm_flags, int mode) {
-  extern __shared__ float hs_prod[];
+  extern __shared__ __align__(16) float hs_prod[];
   __shared__ float s_est[5];  // ex, ey, eth, sin(eth), cos(eth)
   const int slot = P.slot0 + blockIdx.x;
   const int tid = threadIdx.x;
@@ -503,7 +509,7 @@ __global__ void __launch_bounds__(HS_MATCH_THREADS, (PPT > 0 && PPT <= 3) ? 7 : 
         __syncthreads();
         for (int it = 0; it <= L.max_iter; ++it) {  // 1 + maxIterations evaluations, no early exit
           const float cex = s_est[0], cey = s_est[1], csn = s_est[3], ccs = s_est[4];
-          a = hs_eval_cta<STRICT, PPT>(val, L, cex, cey, csn, ccs, pts, preg, cache, n, L.pt_factor, hs_prod, sw, &mt);
+          a = hs_eval_cta<STRICT, PPT>(val, L, cex, cey, csn, ccs, pts, preg, cache, n, L.pt_factor, hs_prod, hs_match2_pitch(P.max_points), sw, &mt);
           if (serial) {
             clamps += hs_gauss_newton_step(a, ex, ey, eth) ? 1u : 0u;
             if (leader) { s_est[0] = ex; s_est[1] = ey; s_est[2] = eth; s_est[3] = hs_sinf(eth); s_est[4] = hs_cosf(eth); }
@@ -542,9 +548,6 @@ __global__ void __launch_bounds__(HS_MATCH_THREADS, (PPT > 0 && PPT <= 3) ? 7 : 
 //   sums    as in hs_eval_cta: lanes 0..8 of warp 0, one dependent FADD chain per sum in the reference's point order.
 // Points, keys and probabilities live in shared memory, so any scan length works with one instantiation.
 // dynamic shared memory: 9 * pitch floats | max_points float4 | max_points float2 | max_points int | max_points ushort.
-__device__ __forceinline__ int hs_match2_pitch(int max_points) {   // >= max_points, == 4 (mod 32): conflict-free 16-byte row reads
-  return ((max_points + 27) & ~31) + 4;
-}
 
 template <bool STRICT>
 __device__ __forceinline__ HsAcc hs_eval_cta2(const float* __restrict__ val, const HsLevel& L, float ex, float ey, float sn, float cs,
@@ -793,13 +796,14 @@ template <bool STRICT>
 __global__ void __launch_bounds__(HS_MATCH_THREADS) k_hessian_derivs(HsParams P, int stream, int level, const float* __restrict__ poses_map,
                                                                      int n_poses, const float2* __restrict__ pts, int n_pts,
                                                                      float* __restrict__ H9, float* __restrict__ dTr3) {
-  extern __shared__ float hs_prod[];
+  extern __shared__ __align__(16) float hs_prod[];
   const int k = blockIdx.x;
   if (k >= n_poses) return;
   const HsLevel& L = P.lv[level];
   const float* val = P.val + (size_t)stream * P.cells_per_stream + L.cell_offset;
   const float th = poses_map[3 * k + 2];
-  HsAcc a = hs_eval_cta<STRICT, 0>(val, L, poses_map[3 * k], poses_map[3 * k + 1], hs_sinf(th), hs_cosf(th), pts, nullptr, nullptr, n_pts, 1.0f, hs_prod);
+  HsAcc a = hs_eval_cta<STRICT, 0>(val, L, poses_map[3 * k], poses_map[3 * k + 1], hs_sinf(th), hs_cosf(th), pts, nullptr, nullptr, n_pts, 1.0f, hs_prod,
+                                   hs_match2_pitch(n_pts));
   if (threadIdx.x == 0) {
     float* h = H9 + 9 * (size_t)k;
     h[0] = a.h00; h[1] = a.h01; h[2] = a.h02;
