@@ -1428,9 +1428,14 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS, 3) k_raycast(HsParams P, i
       const int qpr = ((x1 - x0) >> 2) + 1;     // quads per box row (x0 is 32-aligned, W a multiple of 4)
       const int nq = qpr * rows;
       const int4 mf4 = make_int4(mark_free, mark_free, mark_free, mark_free);
+      // a thread's quads are T apart in the row-major list; its position advances incrementally: c = quad in the row,
+      // ni = nibble index into the cell map (row pitch pw*4 nibbles), gq = cell offset of the quad in the grid
       const int d_ry = T / qpr, d_c = T - d_ry * qpr;   // one stride of T quads, as (rows, quads)
+      const int ni_step = d_ry * (pw << 2) + d_c, gq_step = d_ry * W + (d_c << 2);
+      const int ni_wrap = (pw << 2) - qpr, gq_wrap = W - (qpr << 2);
       int c;
-      int ry = hs_udiv_small(threadIdx.x, qpr, c);
+      const int ry0 = hs_udiv_small(threadIdx.x, qpr, c);
+      int ni = ry0 * (pw << 2) + c, gq = (yb0 + ry0) * W + x0 + (c << 2);
       for (int q0 = threadIdx.x; q0 < nq; q0 += 4 * T) {
         unsigned bits[4];
         int g[4];
@@ -1439,12 +1444,12 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS, 3) k_raycast(HsParams P, i
         for (int u = 0; u < 4; ++u) {
           bits[u] = 0u;
           if (q0 + u * T < nq) {
-            bits[u] = (cmap[ry * pw + (c >> 2)] >> ((unsigned)(c & 3) << 2)) & 0xFu;
-            g[u] = (yb0 + ry) * W + x0 + (c << 2);
-            if (bits[u]) v[u] = *reinterpret_cast<const float4*>(val + g[u]);
+            bits[u] = (cmap[ni >> 2] >> ((unsigned)(ni & 3) << 2)) & 0xFu;
+            g[u] = gq;
+            if (bits[u]) v[u] = *reinterpret_cast<const float4*>(val + gq);
           }
-          ry += d_ry; c += d_c;
-          if (c >= qpr) { c -= qpr; ++ry; }
+          c += d_c; ni += ni_step; gq += gq_step;
+          if (c >= qpr) { c -= qpr; ni += ni_wrap; gq += gq_wrap; }
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
