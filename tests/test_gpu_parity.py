@@ -152,3 +152,32 @@ def test_both_matcher_variants_are_bit_identical(hs, oracle, monkeypatch):
             assert n_diff == 0
     for p in procs:
         p.close()
+
+
+def test_long_closed_loop_64_streams_1000_scans(hs, oracle):
+    """SURVEY section 8(d) parity gate at its full length: 64 streams x 1000 scans (one full loop of the trajectory, node
+    parameters: gate 0.4 m / 0.9 rad, factors 0.4 / 0.9), closed loop. Every pose of every scan and the final maps must equal
+    the CPU oracle bit for bit -- far inside the 1e-4 m / 1e-4 rad / 1e-5 log-odds bar -- and the update indices must agree
+    (so exactly the same scans passed the gate)."""
+    import os
+    n_streams, n_scans = 64, 1000
+    sc, ranges, pts, cnt, truth = make_streams(hs, n_streams, n_scans, seed0=31000)
+    procs = cpu_streams(oracle, n_streams, **NODE)
+    secs, cpu_poses, _ = oracle.run_streams(procs, pts, cnt, threads=os.cpu_count() or 4)
+    with hs.Engine(n_streams=n_streams, max_points=360) as eng:
+        configure(eng, **NODE)
+        for k in range(n_scans):
+            poses, _ = eng.update_batch(pts[k], cnt[k], want_cov=False)
+            assert np.array_equal(bits(poses), bits(cpu_poses[k])), "scan %d: max |dpose| %g" % (k, np.abs(poses - cpu_poses[k]).max())
+        n_diff, _ = compare_maps(eng, procs, 3, exact=True)
+        assert n_diff == 0
+        for s in (0, 17, 63):
+            assert eng.update_index(s, 0) == procs[s].update_index(0)
+        st = eng.stats()
+        assert st["integrations"] == sum(p.integrations() for p in procs)
+        assert 64 * 10 < st["integrations"] < 64 * 400      # the 0.4 m / 0.9 rad gate lets only a fraction of the scans through
+        # the matcher stays locked on: final poses within 15 cm of the simulated truth (relative to the start pose)
+        err = np.linalg.norm(poses[:, :2] - truth[-1, :, :2], axis=1)
+        assert err.max() < 0.15, err.max()
+    for p in procs:
+        p.close()
