@@ -817,8 +817,11 @@ int hs_raycast_batch(hs_engine* e, int n, const int32_t* stream_ids, const float
   const int threads = 128;
   k_force_integrate<<<warp_grid(n, threads), threads, 0, e->stream>>>(e->P, n, d_ids, (const float2*)e->d_points, e->d_counts, d_or, e->d_hints);
   HS_LAUNCHED(e);
-  k_raycast<<<n * e->P.n_levels, HS_RAYCAST_THREADS, raycast_smem(e), e->stream>>>(
-      e->P, n, d_ids, (const float2*)e->d_points, e->d_counts, d_or, raycast_log2_hash(e->P.max_points), e->log2_seg_levels);
+  {
+    ProfScope ps(e, HS_K_RAYCAST);
+    k_raycast<<<n * e->P.n_levels, HS_RAYCAST_THREADS, raycast_smem(e), e->stream>>>(
+        e->P, n, d_ids, (const float2*)e->d_points, e->d_counts, d_or, raycast_log2_hash(e->P.max_points), e->log2_seg_levels);
+  }
   HS_LAUNCHED(e);
   HS_CK(cudaStreamSynchronize(e->stream));
   return HS_OK;

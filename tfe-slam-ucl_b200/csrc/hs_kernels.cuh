@@ -1109,8 +1109,9 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS, 3) k_raycast(HsParams P, i
   const int integrate = P.slot_integrate[slot];
   const int s = hs_slot_stream(stream_ids, slot);
   const HsLevel& L = P.lv[level];
-  float* val = P.val + (size_t)s * P.cells_per_stream + L.cell_offset;
-  int* idx = P.idx + (size_t)s * P.cells_per_stream + L.cell_offset;
+  const int s_map = (P.dbg_skip & 256) ? (s & 7) : s;   // timing experiment (wrong results): all CTAs share 8 streams' grids, which fit in L2
+  float* val = P.val + (size_t)s_map * P.cells_per_stream + L.cell_offset;
+  int* idx = P.idx + (size_t)s_map * P.cells_per_stream + L.cell_offset;
   const int W = L.sx;
   const int T = blockDim.x;
 
@@ -1436,40 +1437,25 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS, 3) k_raycast(HsParams P, i
       int c;
       const int ry0 = hs_udiv_small(threadIdx.x, qpr, c);
       int ni = ry0 * (pw << 2) + c, gq = (yb0 + ry0) * W + x0 + (c << 2);
-      for (int q0 = threadIdx.x; q0 < nq; q0 += 4 * T) {
-        unsigned bits[4];
-        int g[4];
-        float4 v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          bits[u] = 0u;
-          if (q0 + u * T < nq) {
-            bits[u] = (cmap[ni >> 2] >> ((unsigned)(ni & 3) << 2)) & 0xFu;
-            g[u] = gq;
-            if (bits[u]) v[u] = *reinterpret_cast<const float4*>(val + gq);
-          }
-          c += d_c; ni += ni_step; gq += gq_step;
-          if (c >= qpr) { c -= qpr; ni += ni_wrap; gq += gq_wrap; }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (bits[u]) {
-            float4 w = v[u];
-            if (bits[u] & 1u) w.x = w.x + f;
-            if (bits[u] & 2u) w.y = w.y + f;
-            if (bits[u] & 4u) w.z = w.z + f;
-            if (bits[u] & 8u) w.w = w.w + f;
-            *reinterpret_cast<float4*>(val + g[u]) = w;
-            if (bits[u] == 0xFu || (P.dbg_skip & 64)) {   // bit 6 (timing experiment, wrong markers): every quad as one 16-byte store
-              *reinterpret_cast<int4*>(idx + g[u]) = mf4;
-            } else {
-              if (bits[u] & 1u) idx[g[u]] = mark_free;
-              if (bits[u] & 2u) idx[g[u] + 1] = mark_free;
-              if (bits[u] & 4u) idx[g[u] + 2] = mark_free;
-              if (bits[u] & 8u) idx[g[u] + 3] = mark_free;
-            }
+      for (int q0 = threadIdx.x; q0 < nq; q0 += T) {
+        const unsigned bits = (cmap[ni >> 2] >> ((unsigned)(ni & 3) << 2)) & 0xFu;
+        if (bits) {
+          // val += f on the marked cells of the quad as ONE 16-byte floating-point reduction performed in L2 (IEEE round to
+          // nearest, like the FADD of updateSetFree; nothing is loaded into or written back from registers). Unmarked cells
+          // get -0.0f added, which leaves every value -- including +-0.0 -- bit for bit as it was.
+          const float a0 = (bits & 1u) ? f : -0.0f, a1 = (bits & 2u) ? f : -0.0f, a2 = (bits & 4u) ? f : -0.0f, a3 = (bits & 8u) ? f : -0.0f;
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(val + gq), "f"(a0), "f"(a1), "f"(a2), "f"(a3) : "memory");
+          if (bits == 0xFu) {
+            *reinterpret_cast<int4*>(idx + gq) = mf4;
+          } else {
+            if (bits & 1u) idx[gq] = mark_free;
+            if (bits & 2u) idx[gq + 1] = mark_free;
+            if (bits & 4u) idx[gq + 2] = mark_free;
+            if (bits & 8u) idx[gq + 3] = mark_free;
           }
         }
+        c += d_c; ni += ni_step; gq += gq_step;
+        if (c >= qpr) { c -= qpr; ni += ni_wrap; gq += gq_wrap; }
       }
     } else {
       // generic path (any grid width): a lane owns one cell per 32-cell segment
