@@ -1225,6 +1225,7 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS, 3) k_raycast(HsParams P, i
 
   // phase A3: walk list = the owner beam of every end cell. Beams that share an end cell have identical traces (same
   // start, same end), and the owner -- the smallest index -- is the one that decides every "free came first" question.
+  float v_end = 0.0f;   // log-odds of the end cell owned by beam threadIdx.x (first pass of A3)
   for (int i0 = 0; i0 < n; i0 += T) {
     const int i = i0 + threadIdx.x;
     bool owner = false;
@@ -1265,7 +1266,10 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS, 3) k_raycast(HsParams P, i
       w.seg_start = (int)(unsigned)(base & 0xFFFFFFFFULL) + incl - nseg;
       const int pos = (int)(base >> 32) + __popc(m & ((1u << lane) - 1u));
       walk[pos] = w;
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(val + r.kend));   // phase C reads this cell: have it in L2 by then
+      // phase C needs this end cell's log-odds. Nothing else touches an end cell during the scan (the sweep only adds -0.0f
+      // to it), so the load is issued now and consumed after the walk and the sweep: its latency never shows.
+      if (i0 == 0) v_end = __ldcg(val + r.kend);
+      else asm volatile("prefetch.global.L2 [%0];" ::"l"(val + r.kend));
       if (single_band) {   // the whole trace lies in the one band; mark the end cell in the (already cleared) map
         tlo[pos] = 0;
         tlen[pos] = r.da;
@@ -1480,16 +1484,17 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS, 3) k_raycast(HsParams P, i
   hs_stamp(P, 4);
   // phase C: end points -- the owner beam applies undo-free / occupied and stores markOcc
   // (end cells are disjoint from the cells B2 marks: their free bit is never set)
-  for (int wi = threadIdx.x; wi < ((P.dbg_skip & 4) ? 0 : n_walk); wi += T) {
-    const int i = walk[wi].beam & 0x3FFFFFFF;
-    const int kend = beams[i].kend;
-    const int h = hs_hash_find(hkeys, hash_mask, log2_hash, kend);
+  for (int i = threadIdx.x; i < ((P.dbg_skip & 4) ? 0 : n); i += T) {   // same beam-to-thread mapping as phase A3
+    const HsBeamRec r = beams[i];
+    if (r.da == 0) continue;
+    const int h = hs_hash_find(hkeys, hash_mask, log2_hash, r.kend);
     const int hv = hvals[h];
-    float v = val[kend];
+    if ((hv >> 1) != i) continue;      // not the owner of its end cell
+    float v = i < T ? v_end : val[r.kend];
     if (hv & 1) v = (v + f) - f;       // updateSetFree by an earlier beam, then updateUnsetFree
     if (v < 50.0f) v = v + o;          // updateSetOccupied
-    val[kend] = v;
-    idx[kend] = mark_occ;
+    val[r.kend] = v;
+    idx[r.kend] = mark_occ;
   }
   if (P.dbg_times) { __syncthreads(); hs_stamp(P, 5); }
 }
