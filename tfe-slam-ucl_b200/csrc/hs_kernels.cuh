@@ -1449,7 +1449,8 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS, 3) k_raycast(HsParams P, i
           // get -0.0f added, which leaves every value -- including +-0.0 -- bit for bit as it was.
           const float a0 = (bits & 1u) ? f : -0.0f, a1 = (bits & 2u) ? f : -0.0f, a2 = (bits & 4u) ? f : -0.0f, a3 = (bits & 8u) ? f : -0.0f;
           asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(val + gq), "f"(a0), "f"(a1), "f"(a2), "f"(a3) : "memory");
-          if (bits == 0xFu) {
+          if (P.dbg_skip & 8) {   // timing experiment (wrong markers): no free-marker stores
+          } else if (bits == 0xFu || (P.dbg_skip & 64)) {   // bit 6, timing experiment (wrong markers): every quad as one 16-byte store
             *reinterpret_cast<int4*>(idx + gq) = mf4;
           } else {
             if (bits & 1u) idx[gq] = mark_free;
