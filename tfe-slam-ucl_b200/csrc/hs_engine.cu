@@ -188,6 +188,12 @@ int hs_create(const hs_config* cfg, hs_engine** out) {
   P.n_streams = cfg->n_streams;
   P.max_points = cfg->max_points;
   { const char* d = getenv("HSGPU_DEBUG_SKIP"); P.dbg_skip = d ? atoi(d) : 0; }   // timing experiments only: results are wrong when set
+  {
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, cfg->device);
+    P.tail_slots = 2 * n_sm;   // measured on B200 (148 SMs): 0 -> 179 us, 148 -> 178, 296 -> 176, 444 -> 178.5, 600 -> 181
+  }
+  if (const char* ts = getenv("HSGPU_RAYCAST_TAIL_SLOTS")) P.tail_slots = atoi(ts) < 0 ? 0 : atoi(ts);
   P.strict = 1;  // reference-order sums by default: bitwise the CPU reference's poses
 
   // MapRepMultiMap ctor (HSL/slam_main/MapRepMultiMap.h:48-72): same world offset for every level,

@@ -39,6 +39,7 @@ struct HsParams {
   int n_levels;
   int n_streams;
   int max_points;
+  int tail_slots;                   // k_raycast: the last `tail_slots` slots of a launch are dispatched level-major
   int slot0;                        // first slot of this launch (a host batch may be cut into chunks that run on several CUDA streams)
   int dbg_skip;                     // timing experiments only (HSGPU_DEBUG_SKIP): bit0 skip walk, bit1 skip sweep, bit2 skip end points
   unsigned long long* dbg_times;    // timing experiments only (HSGPU_DEBUG_TIMES): 8 globaltimer stamps per ray-cast CTA
@@ -1098,10 +1099,20 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS, 3) k_raycast(HsParams P, i
   // is 20 % slower)
   int level, slot;
   {
-    const int local = blockIdx.x / P.n_levels;
-    level = blockIdx.x - local * P.n_levels;
+    // ... except for the last ~wave of slots, which is dispatched level-major (fine grids first): the launch then drains
+    // through the short coarse-grid CTAs instead of waiting for a few long fine-grid ones
+    const int n_tail = min(n_slots, P.tail_slots), n_head = n_slots - n_tail;
+    int local;
+    if ((int)blockIdx.x < n_head * P.n_levels) {
+      local = blockIdx.x / P.n_levels;
+      level = blockIdx.x - local * P.n_levels;
+    } else {
+      const int r = blockIdx.x - n_head * P.n_levels;
+      level = r / n_tail;
+      local = n_head + (r - level * n_tail);
+    }
     slot = P.slot0 + local;
-    if (local >= n_slots) return;
+    if (local >= n_slots || level >= P.n_levels) return;
   }
   hs_stamp(P, 0);
   // Everything this CTA needs from global memory is requested up front, BEFORE the gate flag is tested: the loads are
@@ -1156,10 +1167,16 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS, 3) k_raycast(HsParams P, i
       v4[i] = make_int4(INT_MAX, INT_MAX, INT_MAX, INT_MAX);
     }
   }
+  {   // ... and the whole cell map (8 16-byte stores per thread, while the prologue's global loads are in flight): the box
+      // is not known yet, and phase A3 sets end-cell bits right after the next barrier
+    uint4* m4 = reinterpret_cast<uint4*>(hs_smem);
+    for (int i = threadIdx.x; i < HS_MAP_BYTES / 16; i += T) m4[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
   if (threadIdx.x == 0) { s_box[0] = INT_MAX; s_box[1] = INT_MAX; s_box[2] = INT_MIN; s_box[3] = INT_MIN; s_alloc = 0ULL; s_visits = 0u; }
   __syncthreads();
 
-  // phase A1: one thread per beam -- beam record and bounding box
+  // phases A1 + A2: one thread per beam -- beam record, bounding box, and end point ownership (io = smallest beam index
+  // per end cell) through the shared hash table
   {
     unsigned visits = 0;
     int xmin = INT_MAX, ymin = INT_MAX, xmax = INT_MIN, ymax = INT_MIN;
@@ -1173,6 +1190,13 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS, 3) k_raycast(HsParams P, i
         visits += b.abs_da + 1u;
         r.da = (unsigned short)b.abs_da;
         xmin = min(xmin, b.ex); xmax = max(xmax, b.ex); ymin = min(ymin, b.ey); ymax = max(ymax, b.ey);
+        int h = hs_hash_slot(b.kend, log2_hash);
+        for (;;) {
+          int old = atomicCAS(&hkeys[h], HS_HASH_EMPTY, b.kend);
+          if (old == HS_HASH_EMPTY || old == b.kend) break;
+          h = (h + 1) & hash_mask;
+        }
+        atomicMin(&hvals[h], i << 1);
       }
       beams[i] = r;
     }
@@ -1202,26 +1226,7 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS, 3) k_raycast(HsParams P, i
   const bool single_band = n_bands == 1;
   const int log2_seg = level == 0 ? (log2_seg_levels & 0xFF) : (log2_seg_levels >> 8);   // per level: fine grid / coarse grids
   const int seg = 1 << log2_seg;
-  if (single_band) {   // clear the part of the cell map this scan uses (A3 sets the end bits after A2's barrier)
-    uint4* m4 = reinterpret_cast<uint4*>(hs_smem);
-    const int n4 = (pw * bh + 3) >> 2;
-    for (int i = threadIdx.x; i < n4; i += T) m4[i] = make_uint4(0u, 0u, 0u, 0u);
-  }
-
   hs_stamp(P, 1);
-  // phase A2: end point ownership -- io = smallest beam index per end cell
-  for (int i = threadIdx.x; i < n; i += T) {
-    const HsBeamRec r = beams[i];
-    if (r.da == 0) continue;
-    int h = hs_hash_slot(r.kend, log2_hash);
-    for (;;) {
-      int old = atomicCAS(&hkeys[h], HS_HASH_EMPTY, r.kend);
-      if (old == HS_HASH_EMPTY || old == r.kend) break;
-      h = (h + 1) & hash_mask;
-    }
-    atomicMin(&hvals[h], i << 1);
-  }
-  __syncthreads();
 
   // phase A3: walk list = the owner beam of every end cell. Beams that share an end cell have identical traces (same
   // start, same end), and the owner -- the smallest index -- is the one that decides every "free came first" question.
