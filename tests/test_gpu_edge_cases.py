@@ -308,9 +308,11 @@ def test_offpath_members_on_random_maps(hs, oracle):
         p.close()
 
 
-def test_pinned_host_batches_are_chunked_and_identical(hs, monkeypatch):
-    """With pinned host buffers hs_update_batch cuts the batch into chunks on several CUDA streams (copy of chunk c+1 under
-    the kernels of chunk c). Results must not depend on the chunking: 1, 2, 3 and 4 chunks, with and without stream_ids."""
+def test_pinned_host_batches_zero_copy_and_chunked_are_identical(hs, monkeypatch):
+    """With pinned host buffers hs_update_batch lets the matcher read the scans straight from host memory (zero-copy, the
+    default) or, with HSGPU_E2E_ZERO_COPY=0, cuts the batch into chunks on several CUDA streams (copy of chunk c+1 under the
+    kernels of chunk c). Results must not depend on the transport: zero-copy, 1, 2, 3 and 4 chunks, with and without
+    stream_ids, all bit-identical."""
     import torch
     n, n_scans = 300, 5
     sc, ranges, pts, cnt, truth = make_streams(hs, n, n_scans, seed0=9000)
@@ -318,8 +320,9 @@ def test_pinned_host_batches_are_chunked_and_identical(hs, monkeypatch):
     h_cnt = torch.from_numpy(cnt).pin_memory()
     ids = torch.from_numpy(np.random.default_rng(3).permutation(n).astype(np.int32)).pin_memory()
     results = []
-    for chunks in ("1", "2", "3", "4"):
-        monkeypatch.setenv("HSGPU_E2E_CHUNKS", chunks)
+    for chunks in ("1", "2", "3", "4", "zero-copy"):
+        monkeypatch.setenv("HSGPU_E2E_ZERO_COPY", "1" if chunks == "zero-copy" else "0")
+        monkeypatch.setenv("HSGPU_E2E_CHUNKS", "2" if chunks == "zero-copy" else chunks)
         for use_ids in (False, True):
             with hs.Engine(n_streams=n, max_points=360) as eng:
                 eng.set_update_factor_free(0.4); eng.set_update_factor_occupied(0.9)

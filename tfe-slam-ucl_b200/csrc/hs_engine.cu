@@ -24,7 +24,7 @@ struct hs_engine {
   cudaStream_t own_stream;
   cudaStream_t stream;
   // host batches are cut into chunks whose host-to-device copies overlap the kernels of the previous chunk
-  int e2e_chunks;
+  int e2e_chunks, e2e_first_pct, e2e_zero_copy;
   cudaStream_t aux_stream[HS_MAX_CHUNKS - 1];
   cudaEvent_t ev_fork, ev_join[HS_MAX_CHUNKS - 1];
   // staging (device) for the host-pointer entry points
@@ -281,6 +281,10 @@ int hs_create(const hs_config* cfg, hs_engine** out) {
     e->e2e_chunks = 2;   // measured on B200 (1024 streams x 360 points, pinned buffers): see DESIGN.md section 5
     if (const char* c = getenv("HSGPU_E2E_CHUNKS")) e->e2e_chunks = atoi(c);
     e->e2e_chunks = e->e2e_chunks < 1 ? 1 : (e->e2e_chunks > HS_MAX_CHUNKS ? HS_MAX_CHUNKS : e->e2e_chunks);
+    e->e2e_first_pct = 100;
+    e->e2e_zero_copy = 1;
+    if (const char* z = getenv("HSGPU_E2E_ZERO_COPY")) e->e2e_zero_copy = atoi(z) != 0;
+    if (const char* c = getenv("HSGPU_E2E_FIRST_PCT")) e->e2e_first_pct = atoi(c) < 5 ? 5 : (atoi(c) > 100 ? 100 : atoi(c));
     cudaError_t err = cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming);
     for (int c = 0; c < HS_MAX_CHUNKS - 1 && err == cudaSuccess; ++c) {
       err = cudaStreamCreateWithFlags(&e->aux_stream[c], cudaStreamNonBlocking);
@@ -465,11 +469,15 @@ static int check_batch(const hs_engine* e, int n) {
 // host batch is cut into chunks); the pointers are those of the WHOLE batch.
 static int run_update_device(hs_engine* e, int n, const int32_t* ids, const float* points, const int32_t* counts,
                              const float* origos, const float* hints, const uint8_t* flags, int mode,
-                             cudaStream_t st = nullptr, int slot0 = 0) {
+                             cudaStream_t st = nullptr, int slot0 = 0, float* stage = nullptr, int32_t* stage_cnt = nullptr) {
   if (n == 0) return HS_OK;
   if (!st) st = e->stream;
   HsParams Pc = e->P;
   Pc.slot0 = slot0;
+  Pc.stage_pts = (float2*)stage;   // non-NULL: `points` is pinned host memory, the matcher stages each scan into `stage`
+  Pc.stage_cnt = stage ? stage_cnt : nullptr;   // non-NULL: `counts` is pinned host memory too
+  const float* points_ray = stage ? stage : points;
+  const int32_t* counts_ray = (stage && stage_cnt) ? stage_cnt : counts;
   struct StreamSwap {   // ProfScope records on e->stream
     hs_engine* e; cudaStream_t saved;
     StreamSwap(hs_engine* en, cudaStream_t s) : e(en), saved(en->stream) { e->stream = s; }
@@ -508,7 +516,7 @@ static int run_update_device(hs_engine* e, int n, const int32_t* ids, const floa
     {
       ProfScope ps(e, HS_K_RAYCAST);
       k_raycast<<<n * e->P.n_levels, HS_RAYCAST_THREADS, raycast_smem(e), st>>>(
-          Pc, n, ids, (const float2*)points, counts, (const float2*)origos, raycast_log2_hash(e->P.max_points), e->log2_seg_levels);
+          Pc, n, ids, (const float2*)points_ray, counts_ray, (const float2*)origos, raycast_log2_hash(e->P.max_points), e->log2_seg_levels);
     }
     HS_LAUNCHED(e);
   }
@@ -573,31 +581,57 @@ static int update_host(hs_engine* e, int n, const int32_t* ids, const float* poi
   HS_CK(cudaSetDevice(e->device));
   const size_t row = (size_t)e->P.max_points * 2;   // floats per slot
   const size_t pbytes = (size_t)n * row * sizeof(float);
-  if ((st = stage_common(e, n, ids, counts, origos, hints, flags)) != HS_OK) return st;
-  // The points are the bulk of the input (2.9 KB per 360-beam scan). With pinned host memory the batch is cut into chunks:
-  // chunk c+1's copy runs on the copy engine while chunk c is matched and ray-cast (streams are independent, so the
-  // chunks' kernels may also overlap each other). Pageable memory is copied in one piece (its copies are staged anyway).
-  int chunks = 1;
-  if (e->e2e_chunks > 1 && n >= 64 * e->e2e_chunks) {
+  // Is the caller's memory pinned (then it is mapped into the device's address space, UVA)?
+  auto mapped = [](const void* p) -> const void* {
     cudaPointerAttributes attr;
-    if (cudaPointerGetAttributes(&attr, points) == cudaSuccess && attr.type == cudaMemoryTypeHost) chunks = e->e2e_chunks;
+    const bool ok = cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer;
     cudaGetLastError();
-  }
+    return ok ? attr.devicePointer : nullptr;
+  };
+  const float* m_points = (const float*)mapped(points);
+  // (the 4 KB of counts still go by DMA: read zero-copy they would put a second, dependent PCIe round trip in front of
+  // every CTA's point fetch -- measured 2.82 M vs 2.89 M scans/s)
+  const int32_t* m_counts = nullptr;
+  if ((st = stage_common(e, n, ids, m_counts ? nullptr : counts, origos, hints, flags)) != HS_OK) return st;
+  // The points are the bulk of the input (2.9 KB per 360-beam scan).
+  // Pinned host memory is mapped into the device's address space (UVA): the matcher CTAs then fetch their scans straight
+  // from the caller's buffer over PCIe -- no staging copy to wait for, the transfer of one stream's points overlaps the
+  // matching of the others -- and leave a device copy for the ray-caster. With HSGPU_E2E_ZERO_COPY=0 pinned batches are
+  // instead copied in chunks on auxiliary streams (chunk c+1's copy under chunk c's kernels; measured slower on B200, see
+  // DESIGN.md section 5). Pageable memory is copied in one piece (its copies are staged by the driver anyway).
   const int32_t* d_ids = ids ? e->d_ids : nullptr;
   const float* d_or = origos ? e->d_origos : nullptr;
   const float* d_hi = hints ? e->d_hints : nullptr;
   const uint8_t* d_fl = flags ? e->d_flags : nullptr;
-  if (chunks > 1) HS_CK(cudaEventRecord(e->ev_fork, e->stream));   // after the small arrays and everything queued before
-  for (int c = 0; c < chunks; ++c) {
-    const int off = (int)((long long)n * c / chunks), cnt = (int)((long long)n * (c + 1) / chunks) - off;
-    cudaStream_t cs = c == 0 ? e->stream : e->aux_stream[c - 1];
-    if (c > 0) HS_CK(cudaStreamWaitEvent(cs, e->ev_fork, 0));
-    HS_CK(cudaMemcpyAsync(e->d_points + off * row, points + off * row, (size_t)cnt * row * sizeof(float), cudaMemcpyHostToDevice, cs));
-    st = run_update_device(e, cnt, d_ids, e->d_points, e->d_counts, d_or, d_hi, d_fl, mode, cs, off);
+  const bool pinned = m_points != nullptr;
+  if (pinned && e->e2e_zero_copy) {
+    st = run_update_device(e, n, d_ids, m_points, m_counts ? m_counts : e->d_counts, d_or, d_hi, d_fl, mode, e->stream, 0, e->d_points,
+                           m_counts ? e->d_counts : nullptr);
     if (st != HS_OK) return st;
-    if (c > 0) {
-      HS_CK(cudaEventRecord(e->ev_join[c - 1], cs));
-      HS_CK(cudaStreamWaitEvent(e->stream, e->ev_join[c - 1], 0));
+  } else {
+    int chunks = 1;
+    if (pinned && e->e2e_chunks > 1 && n >= 64 * e->e2e_chunks) chunks = e->e2e_chunks;
+    if (chunks > 1) HS_CK(cudaEventRecord(e->ev_fork, e->stream));   // after the small arrays and everything queued before
+    for (int c = 0; c < chunks; ++c) {
+      // chunk boundaries: the first chunk may be smaller than the others (e2e_first_pct of an equal share), so that the
+      // first kernels start after a shorter copy
+      auto bound = [&](int k) -> int {
+        if (k <= 0) return 0;
+        if (k >= chunks) return n;
+        const long long first = (long long)n * e->e2e_first_pct / (100LL * chunks);
+        return (int)(first + ((long long)n - first) * (k - 1) / (chunks - 1));
+      };
+      const int off = bound(c), cnt = bound(c + 1) - off;
+      if (cnt <= 0) continue;
+      cudaStream_t cs = c == 0 ? e->stream : e->aux_stream[c - 1];
+      if (c > 0) HS_CK(cudaStreamWaitEvent(cs, e->ev_fork, 0));
+      HS_CK(cudaMemcpyAsync(e->d_points + off * row, points + off * row, (size_t)cnt * row * sizeof(float), cudaMemcpyHostToDevice, cs));
+      st = run_update_device(e, cnt, d_ids, e->d_points, e->d_counts, d_or, d_hi, d_fl, mode, cs, off);
+      if (st != HS_OK) return st;
+      if (c > 0) {
+        HS_CK(cudaEventRecord(e->ev_join[c - 1], cs));
+        HS_CK(cudaStreamWaitEvent(e->stream, e->ev_join[c - 1], 0));
+      }
     }
   }
   e->h2d_bytes += pbytes;
@@ -678,10 +712,17 @@ int hs_update_batch_ranges(hs_engine* e, int n, const int32_t* stream_ids, const
   if ((st = check_ids(e, n, stream_ids)) != HS_OK) return st;
   HS_CK(cudaSetDevice(e->device));
   size_t rbytes = (size_t)n * e->n_beams * sizeof(float);
-  HS_CK(cudaMemcpyAsync(e->d_ranges, ranges, rbytes, cudaMemcpyHostToDevice, e->stream));
+  const float* d_src = e->d_ranges;
+  {   // pinned host memory: k_scan_to_points reads the ranges straight from the caller's buffer (zero-copy, see update_host)
+    cudaPointerAttributes attr;
+    if (e->e2e_zero_copy && cudaPointerGetAttributes(&attr, ranges) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
+      d_src = (const float*)attr.devicePointer;
+    cudaGetLastError();
+  }
+  if (d_src == e->d_ranges) HS_CK(cudaMemcpyAsync(e->d_ranges, ranges, rbytes, cudaMemcpyHostToDevice, e->stream));
   e->h2d_bytes += rbytes;
   if ((st = stage_common(e, n, stream_ids, nullptr, nullptr, pose_hints, map_without_matching)) != HS_OK) return st;
-  st = hs_update_batch_ranges_device(e, n, stream_ids ? e->d_ids : nullptr, e->d_ranges, pose_hints ? e->d_hints : nullptr,
+  st = hs_update_batch_ranges_device(e, n, stream_ids ? e->d_ids : nullptr, d_src, pose_hints ? e->d_hints : nullptr,
                                      map_without_matching ? e->d_flags : nullptr);
   if (st != HS_OK) return st;
   if ((st = fetch_rows(e, e->P.last_pose, stream_ids ? e->d_ids : nullptr, 0, n, 3, poses_out)) != HS_OK) return st;

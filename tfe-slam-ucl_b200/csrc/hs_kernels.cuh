@@ -39,6 +39,9 @@ struct HsParams {
   int n_levels;
   int n_streams;
   int max_points;
+  float2* stage_pts;                // matcher: non-NULL = `points` is pinned HOST memory read over PCIe; each CTA copies its scan here
+                                    // (device, [slot][max_points]) in one pass and everything else reads the copy
+  int32_t* stage_cnt;               // ... and its point count here ([slot]); NULL = `counts` is already device memory
   int tail_slots;                   // k_raycast: the last `tail_slots` slots of a launch are dispatched level-major
   int slot0;                        // first slot of this launch (a host batch may be cut into chunks that run on several CUDA streams)
   int dbg_skip;                     // timing experiments only (HSGPU_DEBUG_SKIP): bit0 skip walk, bit1 skip sweep, bit2 skip end points
@@ -466,6 +469,13 @@ __global__ void __launch_bounds__(HS_MATCH_THREADS, (PPT > 0 && PPT <= 3) ? 7 : 
   int n = counts[slot];
   n = n < 0 ? 0 : (n > P.max_points ? P.max_points : n);
   const float2* pts = points + (size_t)slot * P.max_points;
+  if (P.stage_pts) {   // zero-copy input: fetch this scan from the caller's pinned host buffer once
+    if (P.stage_cnt && tid == 0) P.stage_cnt[slot] = n;
+    float2* stg = P.stage_pts + (size_t)slot * P.max_points;
+    for (int i = tid; i < n; i += blockDim.x) stg[i] = pts[i];
+    __syncthreads();
+    pts = stg;
+  }
   const bool mwm = mwm_flags ? (mwm_flags[slot] != 0) : false;
   float wx, wy, wth;
   if (hints) { wx = hints[3 * slot]; wy = hints[3 * slot + 1]; wth = hints[3 * slot + 2]; }
@@ -699,6 +709,13 @@ __global__ void __launch_bounds__(HS_MATCH_THREADS) k_match2(HsParams P, int n_s
   int n = counts[slot];
   n = n < 0 ? 0 : (n > P.max_points ? P.max_points : n);
   const float2* pts = points + (size_t)slot * P.max_points;
+  if (P.stage_pts) {   // zero-copy input: fetch this scan from the caller's pinned host buffer once
+    if (P.stage_cnt && tid == 0) P.stage_cnt[slot] = n;
+    float2* stg = P.stage_pts + (size_t)slot * P.max_points;
+    for (int i = tid; i < n; i += blockDim.x) stg[i] = pts[i];
+    __syncthreads();
+    pts = stg;
+  }
   const bool mwm = mwm_flags ? (mwm_flags[slot] != 0) : false;
   float wx, wy, wth;
   if (hints) { wx = hints[3 * slot]; wy = hints[3 * slot + 1]; wth = hints[3 * slot + 2]; }
@@ -1400,7 +1417,8 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS, 3) k_raycast(HsParams P, i
             if (hit == 0u) {
               hs_reds_or(waddr, mbit & 0xFFFFu);
             } else if (hit & 0xFFFF0000u) {   // the free trace crosses a cell that is some beam's end point
-              const int yy = k / pitch, xx = k - yy * pitch;
+              int xx;
+              const int yy = hs_udiv_small(k, pitch, xx);   // k < 2^18, pitch < 2^15: exact
               hs_free_hits_end_cell(hkeys, hvals, hash_mask, log2_hash, (yy + yb0) * W + (xx + x0), beam);
             }
             k += off_a;
