@@ -34,17 +34,32 @@ def launches(tag, path):
     shutil.copy(path, os.path.join(HERE, tag + "_launches.csv"))
     rows = [r for r in csv.reader(open(path)) if len(r) > 10]
     idx = {h: i for i, h in enumerate(rows[0])}
-    agg = collections.OrderedDict()
+    # bench.py runs three legs on one engine, each after a reset (k_reset_state + k_clear_cells): inputs resident in HBM (the
+    # leg `value` and `roofline` are measured on), hs_update_batch from pinned host buffers (the matcher then fetches its scans
+    # over PCIe inside the kernel), and hs_update_batch_ranges (adds k_scan_to_points). Shares are reported per leg.
+    legs, cur = [], None
     for r in rows[1:]:
-        agg.setdefault(r[idx["Kernel Name"]].split("(")[0], []).append(float(r[idx["Metric Value"]]) / 1e3)
-    hot = {k: v for k, v in agg.items() if k.startswith(("k_match", "void k_match", "k_raycast", "k_scan_to_points"))}
-    tot = sum(sum(v) for v in hot.values())
+        name = r[idx["Kernel Name"]].split("(")[0]
+        us = float(r[idx["Metric Value"]]) / 1e3
+        if name.startswith("k_reset_state"):
+            cur = collections.OrderedDict()
+            legs.append(cur)
+        if cur is None:
+            cur = collections.OrderedDict()
+            legs.append(cur)
+        cur.setdefault(name, []).append(us)
+    leg_names = ["inputs resident in HBM (bench `value`, `roofline`)", "hs_update_batch, pinned host buffers read zero-copy (bench `e2e`)",
+                 "hs_update_batch_ranges (bench `e2e.ranges_api`)"]
     with open(os.path.join(HERE, tag + "_launches.md"), "w") as f:
         f.write("# %s: every launch with its device time (ncu --metrics gpu__time_duration.sum --clock-control none)\n\n" % tag)
-        f.write("Times are cold-cache and serialised by the profiler: compare SHARES with bench.py's CUDA-event shares, not absolutes.\n\n")
-        f.write("| kernel | launches | avg us | min us | max us | share of hot-path time |\n|---|---|---|---|---|---|\n")
-        for k, v in agg.items():
-            f.write("| %s | %d | %.1f | %.1f | %.1f | %s |\n" % (k, len(v), sum(v) / len(v), min(v), max(v), "%.3f" % (sum(v) / tot) if k in hot else "-"))
+        f.write("Times are cold-cache and serialised by the profiler: compare SHARES with bench.py's CUDA-event shares, not absolutes.\n")
+        for li, agg in enumerate(legs):
+            hot = {k: v for k, v in agg.items() if k.startswith(("k_match", "void k_match", "k_raycast", "k_scan_to_points", "k_cloud_to_points"))}
+            tot = sum(sum(v) for v in hot.values()) or 1.0
+            f.write("\n## leg %d: %s\n\n" % (li + 1, leg_names[li] if li < len(leg_names) else "further launches"))
+            f.write("| kernel | launches | avg us | min us | max us | share of hot-path time |\n|---|---|---|---|---|---|\n")
+            for k, v in agg.items():
+                f.write("| %s | %d | %.1f | %.1f | %.1f | %s |\n" % (k, len(v), sum(v) / len(v), min(v), max(v), "%.3f" % (sum(v) / tot) if k in hot else "-"))
 
 
 def kernels(tag, rep):
