@@ -1,5 +1,5 @@
 """Experiment (GPU): per-phase clock64 accumulators of the matcher CTAs (HSGPU_DEBUG_TIMES; thread 0's view).
-usage: gpu_match_phase_times.py [streams] [scans]   (set HSGPU_MATCH_VARIANT=1|2 selects the matcher; build with make TIMING=1)"""
+usage: gpu_match_phase_times.py [streams] [scans]   (set HSGPU_MATCH_VARIANT=1|2 selects the matcher; build with make EXPERIMENTS=1)"""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

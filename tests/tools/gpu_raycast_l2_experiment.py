@@ -1,4 +1,4 @@
-"""Experiment (GPU): is k_raycast bound by HBM? Teacher-forced ray-casts (work independent of the map content) with the
+"""[needs a library built with `make -C tfe-slam-ucl_b200/csrc EXPERIMENTS=1`] Experiment (GPU): is k_raycast bound by HBM? Teacher-forced ray-casts (work independent of the map content) with the
 grids of all CTAs aliased onto 8 streams' grids (HSGPU_DEBUG_SKIP=256: 84 MB, fits the 126 MB L2) versus the normal layout
 (10.5 GiB). Prints the k_raycast device time per launch from the engine's CUDA events."""
 import os, sys

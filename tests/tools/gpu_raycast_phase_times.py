@@ -1,4 +1,4 @@
-"""Experiment (GPU): per-CTA phase time stamps of k_raycast (HSGPU_DEBUG_TIMES), printed as a phase/occupancy summary.
+"""[needs a library built with `make -C tfe-slam-ucl_b200/csrc EXPERIMENTS=1`] Experiment (GPU): per-CTA phase time stamps of k_raycast (HSGPU_DEBUG_TIMES), printed as a phase/occupancy summary.
 usage: gpu_raycast_phase_times.py [streams] [scans]"""
 import os, sys
 import numpy as np

@@ -23,6 +23,14 @@
 #include "hs_libm_exact.h"
 #include "hsgpu.h"
 
+// Timing-experiment switches (HSGPU_DEBUG_SKIP bits, HSGPU_DEBUG_TIMES stamps) exist only in builds made with
+// `make EXPERIMENTS=1` (which also compiles the matcher's phase clocks in); the product build has none of these branches.
+#ifdef HS_EXPERIMENTS
+#define HS_DBG(P_, mask) ((P_).dbg_skip & (mask))
+#else
+#define HS_DBG(P_, mask) 0
+#endif
+
 struct HsLevel {
   int sx, sy;
   float scale;        // scaleToMap = 1/cellLength                (GridMapBase.h:270)
@@ -264,10 +272,10 @@ __device__ __forceinline__ void hs_acc_add(HsAcc& a, float gx, float gy, float r
   a.h12 += gy * rot;
 }
 
-// timing experiments only (build with `make TIMING=1`, run with HSGPU_DEBUG_TIMES): thread 0 of a matcher CTA accumulates
+// timing experiments only (build with `make EXPERIMENTS=1`, run with HSGPU_DEBUG_TIMES): thread 0 of a matcher CTA accumulates
 // clock64() deltas per phase. Compiles to nothing in the product build.
 struct HsMatchTimer {
-#ifdef HS_MATCH_TIMING
+#ifdef HS_EXPERIMENTS
   long long t, acc[5];
   unsigned long long* out;
   __device__ __forceinline__ void begin(unsigned long long* o) { out = o; if (out && threadIdx.x == 0) { t = clock64(); for (int k = 0; k < 5; ++k) acc[k] = 0; } }
@@ -1058,11 +1066,15 @@ __device__ __forceinline__ unsigned hs_shared_addr(const void* p) {
 }
 
 __device__ __forceinline__ void hs_stamp(const HsParams& P, int k) {
+#ifdef HS_EXPERIMENTS
   if (P.dbg_times && threadIdx.x == 0) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     P.dbg_times[(size_t)blockIdx.x * 8 + k] = t;
   }
+#else
+  (void)P; (void)k;
+#endif
 }
 
 // End-cell hash table in shared memory: open addressing, linear probing, size = power of two >= 2 * max_points.
@@ -1137,7 +1149,7 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS, 3) k_raycast(HsParams P, i
   const int integrate = P.slot_integrate[slot];
   const int s = hs_slot_stream(stream_ids, slot);
   const HsLevel& L = P.lv[level];
-  const int s_map = (P.dbg_skip & 256) ? (s & 7) : s;   // timing experiment (wrong results): all CTAs share 8 streams' grids, which fit in L2
+  const int s_map = HS_DBG(P, 256) ? (s & 7) : s;   // timing experiment (wrong results): all CTAs share 8 streams' grids, which fit in L2
   float* val = P.val + (size_t)s_map * P.cells_per_stream + L.cell_offset;
   int* idx = P.idx + (size_t)s_map * P.cells_per_stream + L.cell_offset;
   const int W = L.sx;
@@ -1383,7 +1395,7 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS, 3) k_raycast(HsParams P, i
     //   cell(t) = k0 + t*off_a + floor((abs_da/2 + t*abs_db) / abs_da) * off_b,  err(t) = (abs_da/2 + t*abs_db) mod abs_da.
     // Marks go to the 2-bit-per-cell map of the band in SHARED memory: the scattered cell visits of a scan never reach
     // L2/HBM.
-    if (!(P.dbg_skip & 1)) {
+    if (!HS_DBG(P, 1)) {
       const int k0 = (by - yb0) * pitch + (bx - x0);   // map address of the start cell (may lie outside this band)
       const int per = (n_items + T - 1) / T;
       // neighbouring lanes take segments ~37 beams apart: lanes that walk adjacent beams at the same radius would hit
@@ -1448,7 +1460,7 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS, 3) k_raycast(HsParams P, i
     if (band == 0) hs_stamp(P, 3);
 
     // phase B2: updateSetFree exactly once per marked cell -- coalesced sweep of the band.
-    if (P.dbg_skip & 2) {
+    if (HS_DBG(P, 2)) {
     } else if (vec_ok) {
       // fast path: the band is a list of aligned 4-cell quads (one float4 of log-odds, 4 map bits), dealt out to the
       // threads in row-major order (a warp's 32 quads are 512 contiguous bytes of a row), four quads in flight per
@@ -1472,8 +1484,8 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS, 3) k_raycast(HsParams P, i
           // get -0.0f added, which leaves every value -- including +-0.0 -- bit for bit as it was.
           const float a0 = (bits & 1u) ? f : -0.0f, a1 = (bits & 2u) ? f : -0.0f, a2 = (bits & 4u) ? f : -0.0f, a3 = (bits & 8u) ? f : -0.0f;
           asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(val + gq), "f"(a0), "f"(a1), "f"(a2), "f"(a3) : "memory");
-          if (P.dbg_skip & 8) {   // timing experiment (wrong markers): no free-marker stores
-          } else if (bits == 0xFu || (P.dbg_skip & 64)) {   // bit 6, timing experiment (wrong markers): every quad as one 16-byte store
+          if (HS_DBG(P, 8)) {   // timing experiment (wrong markers): no free-marker stores
+          } else if (bits == 0xFu || HS_DBG(P, 64)) {   // bit 6, timing experiment (wrong markers): every quad as one 16-byte store
             *reinterpret_cast<int4*>(idx + gq) = mf4;
           } else {
             if (bits & 1u) idx[gq] = mark_free;
@@ -1508,7 +1520,7 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS, 3) k_raycast(HsParams P, i
   hs_stamp(P, 4);
   // phase C: end points -- the owner beam applies undo-free / occupied and stores markOcc
   // (end cells are disjoint from the cells B2 marks: their free bit is never set)
-  for (int i = threadIdx.x; i < ((P.dbg_skip & 4) ? 0 : n); i += T) {   // same beam-to-thread mapping as phase A3
+  for (int i = threadIdx.x; i < (HS_DBG(P, 4) ? 0 : n); i += T) {   // same beam-to-thread mapping as phase A3
     const HsBeamRec r = beams[i];
     if (r.da == 0) continue;
     const int h = hs_hash_find(hkeys, hash_mask, log2_hash, r.kend);
@@ -1520,7 +1532,9 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS, 3) k_raycast(HsParams P, i
     val[r.kend] = v;
     idx[r.kend] = mark_occ;
   }
+#ifdef HS_EXPERIMENTS
   if (P.dbg_times) { __syncthreads(); hs_stamp(P, 5); }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
