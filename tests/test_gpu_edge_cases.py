@@ -377,3 +377,28 @@ def test_point_cloud_entry_point_equals_oracle_pipeline(hs, oracle):
     eng.close()
     for p in procs:
         p.close()
+
+
+def test_odd_grid_sizes_use_the_generic_sweep(hs, oracle):
+    """Grid widths that are not multiples of 4 (500 -> 250 -> 125 cells; 251 -> 125 -> 62) cannot use the 16-byte quad sweep:
+    the per-cell path must give the same bits, closed loop and teacher-forced, rectangular maps and off-centre start included."""
+    for size_x, size_y, levels, res, start in ((500, 500, 3, 0.05, (0.5, 0.5)), (251, 333, 3, 0.1, (0.4, 0.6))):
+        n, n_scans = 3, 10
+        sc, ranges, pts, cnt, truth = make_streams(hs, n, n_scans, seed0=8800 + size_x, scale_to_map=1.0 / res)
+        eng = hs.Engine(res, size_x, size_y, start, levels, n_streams=n, max_points=360)
+        procs = [oracle.CpuProcessor("port", res, size_x, size_y, start, levels) for _ in range(n)]
+        for p in procs + [eng]:
+            p.set_update_factor_free(0.4); p.set_update_factor_occupied(0.9)
+            p.set_map_update_min_dist_diff(0.0); p.set_map_update_min_angle_diff(0.0)
+        for k in range(n_scans):
+            out, _ = eng.update_batch(pts[k], cnt[k])
+            for s, p in enumerate(procs):
+                ref = p.update(pts[k, s], cnt[k, s], hint=p.pose())
+                assert np.array_equal(bits(out[s]), bits(ref)), (size_x, k, s)
+        eng.raycast_batch(pts[0], cnt[0], out)
+        for s, p in enumerate(procs):
+            p.raycast(pts[0, s], out[s], n=int(cnt[0, s]))
+        assert_same_maps(eng, procs, levels)
+        eng.close()
+        for p in procs:
+            p.close()
