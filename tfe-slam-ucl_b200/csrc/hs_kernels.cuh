@@ -128,6 +128,7 @@ __device__ __forceinline__ bool hs_pose_difference_larger_than(float x1, float y
 // One warp per scan; beam_cs holds (cosf(angle_i), sinf(angle_i)) with angle_i the reference's float
 // accumulation, precomputed on the host when the scan geometry is set. Valid beams are compacted in
 // order (ballot + popc), as the reference's push_back loop does.
+#define HS_SCAN_INFLIGHT 12   // 384 beams per pass
 __global__ void __launch_bounds__(128) k_scan_to_points(const float* __restrict__ ranges, int n_slots, int n_beams,
                                                         const float2* __restrict__ beam_cs, float range_min,
                                                         float max_range_for_container, float scale_to_map, int max_points,
@@ -138,18 +139,29 @@ __global__ void __launch_bounds__(128) k_scan_to_points(const float* __restrict_
   const float* r = ranges + (size_t)warp * n_beams;
   float2* out = points + (size_t)warp * max_points;
   int base = 0;
-  for (int i0 = 0; i0 < n_beams; i0 += 32) {
-    int i = i0 + lane;
-    float dist = (i < n_beams) ? r[i] : 0.0f;
-    bool valid = (i < n_beams) && (dist > range_min) && (dist < max_range_for_container);
-    unsigned m = __ballot_sync(0xffffffffu, valid);
-    if (valid) {
-      float d = dist * scale_to_map;
-      float2 cs = beam_cs[i];
-      int pos = base + __popc(m & ((1u << lane) - 1u));
-      if (pos < max_points) out[pos] = make_float2(cs.x * d, cs.y * d);
+  for (int c0 = 0; c0 < n_beams; c0 += 32 * HS_SCAN_INFLIGHT) {
+    // all loads of a chunk are issued before the first is used: `ranges` may be the caller's pinned host buffer read over
+    // PCIe (zero-copy), where one round trip costs microseconds
+    float d_in[HS_SCAN_INFLIGHT];
+#pragma unroll
+    for (int u = 0; u < HS_SCAN_INFLIGHT; ++u) {
+      const int i = c0 + u * 32 + lane;
+      d_in[u] = (i < n_beams) ? r[i] : 0.0f;
     }
-    base += __popc(m);
+#pragma unroll
+    for (int u = 0; u < HS_SCAN_INFLIGHT; ++u) {
+      const int i = c0 + u * 32 + lane;
+      const float dist = d_in[u];
+      bool valid = (i < n_beams) && (dist > range_min) && (dist < max_range_for_container);
+      unsigned m = __ballot_sync(0xffffffffu, valid);
+      if (valid) {
+        float d = dist * scale_to_map;
+        float2 cs = beam_cs[i];
+        int pos = base + __popc(m & ((1u << lane) - 1u));
+        if (pos < max_points) out[pos] = make_float2(cs.x * d, cs.y * d);
+      }
+      base += __popc(m);
+    }
   }
   if (lane == 0) counts[warp] = base < max_points ? base : max_points;
 }
