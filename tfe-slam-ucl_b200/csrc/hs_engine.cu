@@ -469,13 +469,15 @@ static int check_batch(const hs_engine* e, int n) {
 // host batch is cut into chunks); the pointers are those of the WHOLE batch.
 static int run_update_device(hs_engine* e, int n, const int32_t* ids, const float* points, const int32_t* counts,
                              const float* origos, const float* hints, const uint8_t* flags, int mode,
-                             cudaStream_t st = nullptr, int slot0 = 0, float* stage = nullptr, int32_t* stage_cnt = nullptr) {
+                             cudaStream_t st = nullptr, int slot0 = 0, float* stage = nullptr, int32_t* stage_cnt = nullptr,
+                             float* host_pose_out = nullptr) {
   if (n == 0) return HS_OK;
   if (!st) st = e->stream;
   HsParams Pc = e->P;
   Pc.slot0 = slot0;
   Pc.stage_pts = (float2*)stage;   // non-NULL: `points` is pinned host memory, the matcher stages each scan into `stage`
   Pc.stage_cnt = stage ? stage_cnt : nullptr;   // non-NULL: `counts` is pinned host memory too
+  Pc.host_pose_out = host_pose_out;
   const float* points_ray = stage ? stage : points;
   const int32_t* counts_ray = (stage && stage_cnt) ? stage_cnt : counts;
   struct StreamSwap {   // ProfScope records on e->stream
@@ -589,9 +591,11 @@ static int update_host(hs_engine* e, int n, const int32_t* ids, const float* poi
     return ok ? attr.devicePointer : nullptr;
   };
   const float* m_points = (const float*)mapped(points);
-  // (the 4 KB of counts still go by DMA: read zero-copy they would put a second, dependent PCIe round trip in front of
-  // every CTA's point fetch -- measured 2.82 M vs 2.89 M scans/s)
-  const int32_t* m_counts = nullptr;
+  // counts pinned too: read zero-copy as well (the matcher then fetches whole rows, so that the point loads do not depend on
+  // the count's round trip), which takes a small DMA copy and its latency off the front of the call
+  const int32_t* m_counts = (m_points && e->e2e_zero_copy) ? (const int32_t*)mapped(counts) : nullptr;
+  // poses_out pinned: the matcher writes the poses straight into it (no D2H copy behind the last kernel)
+  float* m_poses = (m_points && e->e2e_zero_copy && poses_out && !ids) ? (float*)mapped(poses_out) : nullptr;
   if ((st = stage_common(e, n, ids, m_counts ? nullptr : counts, origos, hints, flags)) != HS_OK) return st;
   // The points are the bulk of the input (2.9 KB per 360-beam scan).
   // Pinned host memory is mapped into the device's address space (UVA): the matcher CTAs then fetch their scans straight
@@ -605,9 +609,22 @@ static int update_host(hs_engine* e, int n, const int32_t* ids, const float* poi
   const uint8_t* d_fl = flags ? e->d_flags : nullptr;
   const bool pinned = m_points != nullptr;
   if (pinned && e->e2e_zero_copy) {
-    st = run_update_device(e, n, d_ids, m_points, m_counts ? m_counts : e->d_counts, d_or, d_hi, d_fl, mode, e->stream, 0, e->d_points,
-                           m_counts ? e->d_counts : nullptr);
-    if (st != HS_OK) return st;
+    // The batch still goes out as `chunks` launches on separate CUDA streams: the CTAs of the first chunk put their PCIe
+    // reads on the wire first, so its scans are matched (and its ray-cast runs) while the later chunks' points still arrive.
+    const int chunks = (e->e2e_chunks > 1 && n >= 64 * e->e2e_chunks) ? e->e2e_chunks : 1;
+    if (chunks > 1) HS_CK(cudaEventRecord(e->ev_fork, e->stream));
+    for (int c = 0; c < chunks; ++c) {
+      const int off = (int)((long long)n * c / chunks), cnt = (int)((long long)n * (c + 1) / chunks) - off;
+      cudaStream_t cs = c == 0 ? e->stream : e->aux_stream[c - 1];
+      if (c > 0) HS_CK(cudaStreamWaitEvent(cs, e->ev_fork, 0));
+      st = run_update_device(e, cnt, d_ids, m_points, m_counts ? m_counts : e->d_counts, d_or, d_hi, d_fl, mode, cs, off, e->d_points,
+                             m_counts ? e->d_counts : nullptr, m_poses);
+      if (st != HS_OK) return st;
+      if (c > 0) {
+        HS_CK(cudaEventRecord(e->ev_join[c - 1], cs));
+        HS_CK(cudaStreamWaitEvent(e->stream, e->ev_join[c - 1], 0));
+      }
+    }
   } else {
     int chunks = 1;
     if (pinned && e->e2e_chunks > 1 && n >= 64 * e->e2e_chunks) chunks = e->e2e_chunks;
@@ -635,7 +652,8 @@ static int update_host(hs_engine* e, int n, const int32_t* ids, const float* poi
     }
   }
   e->h2d_bytes += pbytes;
-  if ((st = fetch_rows(e, e->P.last_pose, ids ? e->d_ids : nullptr, 0, n, 3, poses_out)) != HS_OK) return st;
+  if (pinned && e->e2e_zero_copy && m_poses) e->d2h_bytes += (size_t)n * 3 * sizeof(float);
+  else if ((st = fetch_rows(e, e->P.last_pose, ids ? e->d_ids : nullptr, 0, n, 3, poses_out)) != HS_OK) return st;
   if (cov_out) {
     if (ids && poses_out) HS_CK(cudaStreamSynchronize(e->stream));  // d_out is reused by the second gather
     if ((st = fetch_rows(e, e->P.cov, ids ? e->d_ids : nullptr, 0, n, 9, cov_out)) != HS_OK) return st;

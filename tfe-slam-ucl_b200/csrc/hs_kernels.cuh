@@ -50,6 +50,7 @@ struct HsParams {
   float2* stage_pts;                // matcher: non-NULL = `points` is pinned HOST memory read over PCIe; each CTA copies its scan here
                                     // (device, [slot][max_points]) in one pass and everything else reads the copy
   int32_t* stage_cnt;               // ... and its point count here ([slot]); NULL = `counts` is already device memory
+  float* host_pose_out;             // non-NULL: the caller's pinned poses_out [slot][3]; the matcher's tail writes the pose there too
   int tail_slots;                   // k_raycast: the last `tail_slots` slots of a launch are dispatched level-major
   int slot0;                        // first slot of this launch (a host batch may be cut into chunks that run on several CUDA streams)
   int dbg_skip;                     // timing experiments only (HSGPU_DEBUG_SKIP): bit0 skip walk, bit1 skip sweep, bit2 skip end points
@@ -441,6 +442,7 @@ __device__ __forceinline__ bool hs_gauss_newton_step(const HsAcc& a, float& ex, 
 // poseDifferenceLargerThan gate, and -- if the scan is to be integrated -- the update epoch the ray-caster works in.
 __device__ __forceinline__ void hs_match_tail(const HsParams& P, int slot, int s, float wx, float wy, float wth, bool mwm, int mode) {
   P.last_pose[3 * s] = wx; P.last_pose[3 * s + 1] = wy; P.last_pose[3 * s + 2] = wth;
+  if (P.host_pose_out) { P.host_pose_out[3 * slot] = wx; P.host_pose_out[3 * slot + 1] = wy; P.host_pose_out[3 * slot + 2] = wth; }
   int integrate = 0;
   if (mode == 0) {
     float ux = P.last_update_pose[3 * s], uy = P.last_update_pose[3 * s + 1], uth = P.last_update_pose[3 * s + 2];
@@ -492,7 +494,9 @@ __global__ void __launch_bounds__(HS_MATCH_THREADS, (PPT > 0 && PPT <= 3) ? 7 : 
   if (P.stage_pts) {   // zero-copy input: fetch this scan from the caller's pinned host buffer once
     if (P.stage_cnt && tid == 0) P.stage_cnt[slot] = n;
     float2* stg = P.stage_pts + (size_t)slot * P.max_points;
-    for (int i = tid; i < n; i += blockDim.x) stg[i] = pts[i];
+    // counts on the host too: fetch the whole row, so that the point loads do not wait for the count's round trip
+    const int n_fetch = P.stage_cnt ? P.max_points : n;
+    for (int i = tid; i < n_fetch; i += blockDim.x) stg[i] = pts[i];
     __syncthreads();
     pts = stg;
   }
@@ -732,7 +736,9 @@ __global__ void __launch_bounds__(HS_MATCH_THREADS) k_match2(HsParams P, int n_s
   if (P.stage_pts) {   // zero-copy input: fetch this scan from the caller's pinned host buffer once
     if (P.stage_cnt && tid == 0) P.stage_cnt[slot] = n;
     float2* stg = P.stage_pts + (size_t)slot * P.max_points;
-    for (int i = tid; i < n; i += blockDim.x) stg[i] = pts[i];
+    // counts on the host too: fetch the whole row, so that the point loads do not wait for the count's round trip
+    const int n_fetch = P.stage_cnt ? P.max_points : n;
+    for (int i = tid; i < n_fetch; i += blockDim.x) stg[i] = pts[i];
     __syncthreads();
     pts = stg;
   }
