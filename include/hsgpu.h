@@ -109,6 +109,17 @@ int hs_update_batch(hs_engine* e, int n, const int32_t* stream_ids, const float*
 int hs_update_batch_device(hs_engine* e, int n, const int32_t* stream_ids, const float* points, const int32_t* counts,
                            const float* origos, const float* pose_hints, const uint8_t* map_without_matching);
 
+/* Pipelined submission -- update() for n streams WITHOUT waiting for the result (no reference counterpart: the reference's
+ * update() is synchronous; this is what a server feeding queued scans uses). The inputs are copied by DMA on a copy stream
+ * into one of two staging sets, so that batch k+1's transfer overlaps batch k's matching and integration; poses_out (or
+ * NULL) is written by the matcher. ALL host buffers must be pinned and must not be touched until hs_wait(); with pageable
+ * memory the call degrades to the synchronous hs_update_batch. Pose hints default to each stream's last pose ON THE
+ * DEVICE, so consecutive scans of the same streams can be submitted back to back. Results are identical to hs_update_batch. */
+int hs_submit_batch(hs_engine* e, int n, const int32_t* stream_ids, const float* points, const int32_t* counts,
+                    const float* origos, const float* pose_hints, const uint8_t* map_without_matching, float* poses_out);
+/* Returns when everything submitted so far has completed and its outputs are in place. */
+int hs_wait(hs_engine* e);
+
 /* LaserScan ingestion (HectorMappingRos::rosLaserScanToDataContainer, src/hector_slam/hector_mapping/src/
  * HectorMappingRos.cpp:483-507) fused in front of update: ranges [n][n_beams] -> points on device.
  * hs_set_scan_geometry fixes sensor_msgs/LaserScan's angle_min, angle_increment, range_min, range_max. */

@@ -402,3 +402,53 @@ def test_odd_grid_sizes_use_the_generic_sweep(hs, oracle):
         eng.close()
         for p in procs:
             p.close()
+
+
+def test_pipelined_submission_equals_synchronous_updates(hs):
+    """hs_submit_batch / hs_wait: scans of the same streams submitted back to back without waiting (inputs double-buffered
+    on a copy stream) give bit for bit the poses and maps of synchronous hs_update_batch calls -- full batches, a stream
+    subset with stream_ids, per-scan pose buffers -- and pageable buffers degrade to the synchronous call."""
+    import torch
+    n, n_scans = 200, 12
+    sc, ranges, pts, cnt, truth = make_streams(hs, n, n_scans, seed0=12345)
+    h_pts = torch.from_numpy(pts).pin_memory()
+    h_cnt = torch.from_numpy(cnt).pin_memory()
+    sub = torch.from_numpy(np.arange(0, n, 3, dtype=np.int32)).pin_memory()
+    sub_pts = torch.from_numpy(np.ascontiguousarray(pts[:, ::3])).pin_memory()
+    sub_cnt = torch.from_numpy(np.ascontiguousarray(cnt[:, ::3])).pin_memory()
+    def make():
+        eng = hs.Engine(n_streams=n, max_points=360)
+        eng.set_update_factor_free(0.4); eng.set_update_factor_occupied(0.9)
+        eng.set_map_update_min_dist_diff(0.0); eng.set_map_update_min_angle_diff(0.0)
+        return eng
+    with make() as a, make() as b:
+        ref = np.zeros((n_scans, n, 3), np.float32)
+        for k in range(n_scans):
+            if k % 4 == 3:   # every 4th scan only for a third of the streams
+                out, _ = a.update_batch(pts[k, ::3], cnt[k, ::3], stream_ids=sub.numpy(), want_cov=False)
+                ref[k, ::3] = out
+            else:
+                ref[k], _ = a.update_batch(pts[k], cnt[k], want_cov=False)
+        got = torch.zeros((n_scans, n, 3), dtype=torch.float32).pin_memory()
+        got_sub = torch.zeros((n_scans, len(sub), 3), dtype=torch.float32).pin_memory()
+        for k in range(n_scans):   # all submitted before anything is waited for
+            if k % 4 == 3:
+                b.submit_batch_raw(len(sub), sub_pts[k].data_ptr(), sub_cnt[k].data_ptr(), got_sub[k].data_ptr(), ids_ptr=sub.data_ptr())
+            else:
+                b.submit_batch_raw(n, h_pts[k].data_ptr(), h_cnt[k].data_ptr(), got[k].data_ptr())
+        b.wait()
+        for k in range(n_scans):
+            if k % 4 == 3:
+                assert np.array_equal(bits(got_sub[k].numpy()), bits(ref[k, ::3])), k
+            else:
+                assert np.array_equal(bits(got[k].numpy()), bits(ref[k])), k
+        assert np.array_equal(bits(a.poses()), bits(b.poses()))
+        for s_ in (0, 3, n - 1):
+            for l in range(3):
+                assert np.array_equal(a.download_level(s_, l), b.download_level(s_, l))
+        # pageable buffers: same results through the synchronous fallback
+        out_pageable = np.zeros((n, 3), np.float32)
+        extra_pts, extra_cnt = np.ascontiguousarray(pts[0]), np.ascontiguousarray(cnt[0])
+        b.submit_batch_raw(n, extra_pts.ctypes.data, extra_cnt.ctypes.data, out_pageable.ctypes.data)
+        ref_extra, _ = a.update_batch(pts[0], cnt[0], want_cov=False)
+        assert np.array_equal(bits(out_pageable), bits(ref_extra))

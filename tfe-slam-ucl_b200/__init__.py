@@ -110,6 +110,7 @@ def lib():
         "hs_set_cuda_stream": (_I, [_P, _P]), "hs_synchronize": (_I, [_P]), "hs_status_string": (ctypes.c_char_p, [_I]),
         "hs_update_batch": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
         "hs_update_batch_device": (_I, [_P, _I, _P, _P, _P, _P, _P, _P]),
+        "hs_submit_batch": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _P]), "hs_wait": (_I, [_P]),
         "hs_set_scan_geometry": (_I, [_P, _I, _F, _F, _F, _F]),
         "hs_update_batch_ranges": (_I, [_P, _I, _P, _P, _P, _P, _P, _P]),
         "hs_update_batch_ranges_device": (_I, [_P, _I, _P, _P, _P, _P]),
@@ -283,6 +284,13 @@ class Engine:
         """hs_update_batch with raw host addresses (pinned buffers in bench.py)."""
         _check(lib().hs_update_batch(self._h, n, ids_ptr, points_ptr, counts_ptr, origos_ptr, hints_ptr, flags_ptr,
                                      poses_out_ptr, cov_out_ptr), "hs_update_batch")
+
+    def submit_batch_raw(self, n, points_ptr, counts_ptr, poses_out_ptr=None, origos_ptr=None, hints_ptr=None, flags_ptr=None, ids_ptr=None):
+        """hs_submit_batch with raw PINNED host addresses: returns at once, results are in place after wait()."""
+        _check(lib().hs_submit_batch(self._h, n, ids_ptr, points_ptr, counts_ptr, origos_ptr, hints_ptr, flags_ptr, poses_out_ptr),
+               "hs_submit_batch")
+
+    def wait(self): _check(lib().hs_wait(self._h), "hs_wait")
 
     def update_batch_device(self, n, points_dptr, counts_dptr, origos_dptr=None, hints_dptr=None, flags_dptr=None, ids_dptr=None):
         _check(lib().hs_update_batch_device(self._h, n, ids_dptr, points_dptr, counts_dptr, origos_dptr, hints_dptr, flags_dptr),

@@ -36,6 +36,12 @@ struct hs_engine {
   int32_t* d_ids;
   float* d_ranges;
   float* d_out;      // [n_streams][9] gather scratch
+  // pipelined submission (hs_submit_batch): two sets of input staging buffers filled by DMA on a copy stream while the
+  // previous batch computes; allocated on first use
+  struct PipeBuf { float* points; int32_t* counts; float* origos; float* hints; uint8_t* flags; int32_t* ids; cudaEvent_t staged, consumed; };
+  PipeBuf pipe[2];
+  cudaStream_t copy_stream;
+  uint64_t submits;
   float2* d_beam_cs; // scan geometry
   int n_beams;
   float range_min, max_range_for_container, angle_min, angle_increment, range_max;
@@ -370,6 +376,13 @@ int hs_destroy(hs_engine* e) {
                   e->d_beam_cs, e->d_scratch};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  if (e->copy_stream) { cudaStreamSynchronize(e->copy_stream); cudaStreamDestroy(e->copy_stream); }
+  for (int b = 0; b < 2; ++b) {
+    void* pp[] = {e->pipe[b].points, e->pipe[b].counts, e->pipe[b].origos, e->pipe[b].hints, e->pipe[b].flags, e->pipe[b].ids};
+    for (void* q : pp) if (q) cudaFree(q);
+    if (e->pipe[b].staged) cudaEventDestroy(e->pipe[b].staged);
+    if (e->pipe[b].consumed) cudaEventDestroy(e->pipe[b].consumed);
+  }
   for (int c = 0; c < HS_MAX_CHUNKS - 1; ++c) {
     if (e->aux_stream[c]) { cudaStreamSynchronize(e->aux_stream[c]); cudaStreamDestroy(e->aux_stream[c]); }
     if (e->ev_join[c]) cudaEventDestroy(e->ev_join[c]);
@@ -672,6 +685,80 @@ int hs_match_batch(hs_engine* e, int n, const int32_t* stream_ids, const float* 
                    const float* origos, const float* pose_hints, float* poses_out, float* cov_out) {
   return update_host(e, n, stream_ids, points, counts, origos, pose_hints, nullptr, poses_out, cov_out, 1);
 }
+
+// ---- pipelined submission ---------------------------------------------------------------------------
+
+static int pipe_init(hs_engine* e) {
+  if (e->copy_stream) return HS_OK;
+  const size_t ns = (size_t)e->P.n_streams, mp = (size_t)e->P.max_points;
+  HS_CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+  for (int b = 0; b < 2; ++b) {
+    hs_engine::PipeBuf& B = e->pipe[b];
+    HS_CK(cudaMalloc((void**)&B.points, ns * mp * 2 * sizeof(float)));
+    HS_CK(cudaMalloc((void**)&B.counts, ns * sizeof(int32_t)));
+    HS_CK(cudaMalloc((void**)&B.origos, ns * 2 * sizeof(float)));
+    HS_CK(cudaMalloc((void**)&B.hints, ns * 3 * sizeof(float)));
+    HS_CK(cudaMalloc((void**)&B.flags, ns * sizeof(uint8_t)));
+    HS_CK(cudaMalloc((void**)&B.ids, ns * sizeof(int32_t)));
+    HS_CK(cudaEventCreateWithFlags(&B.staged, cudaEventDisableTiming));
+    HS_CK(cudaEventCreateWithFlags(&B.consumed, cudaEventDisableTiming));
+  }
+  return HS_OK;
+}
+
+// update() for n streams WITHOUT waiting for the result: the inputs are copied by DMA on a copy stream into one of two
+// staging sets -- so batch k+1's transfer runs while batch k is matched and ray-cast -- and the kernels are queued behind it.
+// All host buffers must be pinned and stay untouched until hs_wait(); poses_out (pinned, or NULL) is written by the
+// matcher itself. Pose hints default to each stream's last pose on the device, so consecutive scans of the same streams
+// can be submitted back to back. Anything else falls back to the synchronous hs_update_batch.
+int hs_submit_batch(hs_engine* e, int n, const int32_t* stream_ids, const float* points, const int32_t* counts, const float* origos,
+                    const float* pose_hints, const uint8_t* map_without_matching, float* poses_out) {
+  int st = check_batch(e, n);
+  if (st != HS_OK) return st;
+  if (n == 0) return HS_OK;
+  if (!points || !counts) return HS_ERR_INVALID_ARG;
+  if ((st = check_ids(e, n, stream_ids)) != HS_OK) return st;
+  HS_CK(cudaSetDevice(e->device));
+  auto mapped = [](const void* p) -> void* {
+    cudaPointerAttributes attr;
+    const bool ok = p && cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer;
+    cudaGetLastError();
+    return ok ? attr.devicePointer : nullptr;
+  };
+  float* m_poses = (float*)mapped(poses_out);
+  const bool all_pinned = mapped(points) && mapped(counts) && (!poses_out || m_poses) && (!stream_ids || mapped(stream_ids)) &&
+                          (!origos || mapped(origos)) && (!pose_hints || mapped(pose_hints)) && (!map_without_matching || mapped(map_without_matching));
+  if (!all_pinned) return hs_update_batch(e, n, stream_ids, points, counts, origos, pose_hints, map_without_matching, poses_out, nullptr);
+  if ((st = pipe_init(e)) != HS_OK) return st;
+  hs_engine::PipeBuf& B = e->pipe[e->submits & 1];
+  const size_t row = (size_t)e->P.max_points * 2;
+  cudaStream_t cp = e->copy_stream;
+  HS_CK(cudaStreamWaitEvent(cp, B.consumed, 0));   // the batch that last used this staging set has been computed (no-op the first time)
+  HS_CK(cudaMemcpyAsync(B.points, points, (size_t)n * row * sizeof(float), cudaMemcpyHostToDevice, cp));
+  HS_CK(cudaMemcpyAsync(B.counts, counts, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, cp));
+  size_t bytes = (size_t)n * (row * sizeof(float) + 4);
+  if (stream_ids) { HS_CK(cudaMemcpyAsync(B.ids, stream_ids, (size_t)n * 4, cudaMemcpyHostToDevice, cp)); bytes += (size_t)n * 4; }
+  if (origos) { HS_CK(cudaMemcpyAsync(B.origos, origos, (size_t)n * 8, cudaMemcpyHostToDevice, cp)); bytes += (size_t)n * 8; }
+  if (pose_hints) { HS_CK(cudaMemcpyAsync(B.hints, pose_hints, (size_t)n * 12, cudaMemcpyHostToDevice, cp)); bytes += (size_t)n * 12; }
+  if (map_without_matching) { HS_CK(cudaMemcpyAsync(B.flags, map_without_matching, (size_t)n, cudaMemcpyHostToDevice, cp)); bytes += (size_t)n; }
+  e->h2d_bytes += bytes;
+  HS_CK(cudaEventRecord(B.staged, cp));
+  HS_CK(cudaStreamWaitEvent(e->stream, B.staged, 0));
+  st = run_update_device(e, n, stream_ids ? B.ids : nullptr, B.points, B.counts, origos ? B.origos : nullptr, pose_hints ? B.hints : nullptr,
+                         map_without_matching ? B.flags : nullptr, 0, e->stream, 0, nullptr, nullptr, stream_ids ? nullptr : m_poses);
+  if (st != HS_OK) return st;
+  if (m_poses && stream_ids) {   // poses of a stream subset: gathered on the device, then written to the pinned buffer
+    k_gather_rows<<<(n * 3 + 255) / 256, 256, 0, e->stream>>>(e->P.last_pose, B.ids, n, 3, m_poses);
+    HS_LAUNCHED(e);
+  }
+  if (m_poses) e->d2h_bytes += (size_t)n * 12;
+  HS_CK(cudaEventRecord(B.consumed, e->stream));
+  e->submits++;
+  return HS_OK;
+}
+
+// Waits until everything submitted so far (and every other call on this engine) has completed and its outputs are in place.
+int hs_wait(hs_engine* e) { return hs_synchronize(e); }
 
 int hs_set_scan_geometry(hs_engine* e, int n_beams, float angle_min, float angle_increment, float range_min, float range_max) {
   if (!e || n_beams < 1 || n_beams > e->P.max_points) return HS_ERR_INVALID_ARG;
