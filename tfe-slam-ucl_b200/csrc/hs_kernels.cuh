@@ -990,24 +990,26 @@ __global__ void __launch_bounds__(128) k_occupancy_ray(HsParams P, int stream, i
 // One CTA owns one (stream, level) and runs barrier-separated phases over all beams; everything the beams
 // share while the scan is being traced lives in SHARED memory, the grids in HBM only see the final,
 // coalesced updates:
-//   A1  per beam: end cell, Bresenham parameters -> beam record; bounding box of the scan
-//   A2  per beam: end cell -> shared hash table (cell -> smallest beam index io, via atomicMin) and the
-//       end-cell bit of the CTA's cell map
+//   prologue  every global input of the CTA is requested before the gate flag is tested (one memory round trip); the hash
+//             table and the cell map are cleared while those loads are in flight
+//   A1+A2  per beam: end cell, Bresenham parameters -> beam record; bounding box of the scan; end cell -> shared hash
+//          table (cell -> smallest beam index io, via atomicMin)
 //   A3  beams that share an end cell have identical traces (same start, same end): only the owner io of each end
 //       cell -- the smallest index, which is also the one that decides every "free came first" question -- is put
-//       on the walk list (on the coarse levels this removes more than half of the beams)
-//   B1  free cells of all beams: one thread walks one beam with the reference's bresenham2D recurrence
+//       on the walk list (on the coarse levels this removes more than half of the beams), its end-cell bit is set in
+//       the cell map, its trace is cut into segments, and the load of its end cell's log-odds is issued (used in C)
+//   B1  free cells: the segments are dealt out evenly to the threads, each runs the reference's bresenham2D recurrence
 //       (OccGridMapBase.h:243-260) -- but in a 2-bit-per-cell map of the bounding box held in SHARED memory
-//       (free bit set with a shared-memory atomicOr, skipped when already set): the ~49 k scattered cell visits of a
+//       (free bit set with a shared-memory atomicOr, skipped when already set): the scattered cell visits of a
 //       scan never reach L2/HBM. A free cell that is some beam's end cell (end bit) looks io up in the hash
 //       table and, if this beam < io, sets the entry's "free came first" flag.
-//   B2  coalesced sweep of the box: free bit set -> idx = markFree, val += f  (exactly once per cell)
+//   B2  coalesced sweep of the box, one aligned 4-cell quad per thread and turn: val += f as one 16-byte fp32 reduction
+//       performed in L2 (-0.0f for the unmarked cells of the quad), idx = markFree  (exactly once per cell)
 //   C   end points: the beam that owns io applies undo-free / occupied to val and stores markOcc.
-// If the bounding box does not fit the cell map (HS_MAP_CELLS cells) B1/B2 fall back to marking in the
-// global marker plane: idx = markFree by plain store (idempotent), then the sweep applies f where
-// idx == markFree (only this scan can have written that value); end cells are recognised by a hash probe.
-// No scratch value is ever stored in the grids, and no global atomic is used. A beam's own trace never
-// contains its own end point (bresenham2D visits abs_da cells from the start).
+// A bounding box with more cells than the map holds (HS_MAP_CELLS) is processed in horizontal bands of rows: a trace is
+// monotone in y, so its steps inside a band are one interval with a closed form; segments, B1 and B2 run once per band.
+// No scratch value is ever stored in the grids. A beam's own trace never contains its own end point (bresenham2D visits
+// abs_da cells from the start).
 
 #define HS_HASH_EMPTY (-1)
 #define HS_MAP_BYTES 49152                 // shared-memory cell map: 2 bits per cell, 16 cells per 32-bit word
