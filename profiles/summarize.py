@@ -34,9 +34,10 @@ def launches(tag, path):
     shutil.copy(path, os.path.join(HERE, tag + "_launches.csv"))
     rows = [r for r in csv.reader(open(path)) if len(r) > 10]
     idx = {h: i for i, h in enumerate(rows[0])}
-    # bench.py runs three legs on one engine, each after a reset (k_reset_state + k_clear_cells): inputs resident in HBM (the
+    # bench.py runs four legs on one engine, each after a reset (k_reset_state + k_clear_cells): inputs resident in HBM (the
     # leg `value` and `roofline` are measured on), hs_update_batch from pinned host buffers (the matcher then fetches its scans
-    # over PCIe inside the kernel), and hs_update_batch_ranges (adds k_scan_to_points). Shares are reported per leg.
+    # over PCIe inside the kernel), hs_update_batch_ranges (adds k_scan_to_points) and the pipelined hs_submit_batch. Shares are
+    # reported per leg.
     legs, cur = [], None
     for r in rows[1:]:
         name = r[idx["Kernel Name"]].split("(")[0]
@@ -49,7 +50,7 @@ def launches(tag, path):
             legs.append(cur)
         cur.setdefault(name, []).append(us)
     leg_names = ["inputs resident in HBM (bench `value`, `roofline`)", "hs_update_batch, pinned host buffers read zero-copy (bench `e2e`)",
-                 "hs_update_batch_ranges (bench `e2e.ranges_api`)"]
+                 "hs_update_batch_ranges (bench `e2e.ranges_api`)", "hs_submit_batch / hs_wait, DMA on a copy stream (bench `e2e.pipelined_api`)"]
     with open(os.path.join(HERE, tag + "_launches.md"), "w") as f:
         f.write("# %s: every launch with its device time (ncu --metrics gpu__time_duration.sum --clock-control none)\n\n" % tag)
         f.write("Times are cold-cache and serialised by the profiler: compare SHARES with bench.py's CUDA-event shares, not absolutes.\n")
