@@ -65,3 +65,56 @@ def test_facade_matches_oracle(tmp_path, hs, oracle):
         ref = p.download_level(l)
         assert (sx, sy) == p.level_dims(l)[:2] and ui == p.update_index(l)
         assert np.array_equal(cells["updateIndex"], ref["updateIndex"]) and np.array_equal(bits(cells["logOddsVal"]), bits(ref["logOddsVal"]))
+
+
+def build_batch_test(tmp_path, hs):
+    exe = str(tmp_path / "batch_test")
+    libdir = os.path.dirname(hs.LIB_PATH)
+    cmd = ["g++", "-std=c++14", "-O2", "-I", os.path.join(ROOT, "include"), "-o", exe, os.path.join(ROOT, "tests", "cpp", "batch_test.cpp"),
+           "-L", libdir, "-lhsgpu", "-Wl,-rpath," + libdir, "-pthread"]
+    subprocess.run(cmd, check=True)
+    return exe
+
+
+def test_batch_engine_compiles_and_fails_loudly_without_gpu(tmp_path, hs):
+    """include/hsgpu/BatchEngine.h (C++ RAII wrapper over the C ABI) needs nothing but the C++ standard library."""
+    exe = build_batch_test(tmp_path, hs)
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by test_batch_engine_matches_oracle")
+    inp = tmp_path / "in.bin"
+    inp.write_bytes(np.array([2, 0, 4], np.int32).tobytes())
+    res = subprocess.run([exe, str(inp), str(tmp_path / "out.bin")], capture_output=True, text=True)
+    assert res.returncode == 1 and "no usable CUDA device" in res.stderr
+
+
+@pytest.mark.gpu
+def test_batch_engine_matches_oracle(tmp_path, hs, oracle):
+    exe = build_batch_test(tmp_path, hs)
+    n, n_scans, mp = 5, 9, 360
+    sc, ranges, pts, cnt, truth = make_streams(hs, n, n_scans, seed0=4040)
+    with open(tmp_path / "in.bin", "wb") as f:
+        f.write(np.array([n, n_scans, mp], np.int32).tobytes())
+        for k in range(n_scans):
+            f.write(cnt[k].astype(np.int32).tobytes())
+            f.write(pts[k].astype(np.float32).tobytes())
+    res = subprocess.run([exe, str(tmp_path / "in.bin"), str(tmp_path / "out.bin")], capture_output=True, text=True)
+    assert res.returncode == 0, (res.returncode, res.stderr)
+    raw = open(tmp_path / "out.bin", "rb").read()
+    poses = np.frombuffer(raw[: n_scans * n * 12], np.float32).reshape(n_scans, n, 3)
+    procs = [oracle.CpuProcessor("port") for _ in range(n)]
+    for p in procs:
+        p.set_update_factor_free(0.4); p.set_update_factor_occupied(0.9)
+        p.set_map_update_min_dist_diff(0.0); p.set_map_update_min_angle_diff(0.0)
+    for k in range(n_scans):
+        for s, p in enumerate(procs):
+            assert np.array_equal(bits(poses[k, s]), bits(p.update(pts[k, s], cnt[k, s], hint=p.pose()))), (k, s)
+    off = n_scans * n * 12
+    for s in (0, n - 1):
+        ui = np.frombuffer(raw[off: off + 4], np.int32)[0]
+        off += 4
+        cells = np.frombuffer(raw[off: off + 1024 * 1024 * 8], oracle.CELL_DTYPE)
+        off += 1024 * 1024 * 8
+        ref = procs[s].download_level(0)
+        assert ui == procs[s].update_index(0)
+        assert np.array_equal(cells["updateIndex"], ref["updateIndex"]) and np.array_equal(bits(cells["logOddsVal"]), bits(ref["logOddsVal"]))
