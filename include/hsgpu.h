@@ -166,6 +166,12 @@ const float* hs_device_pose_ptr(const hs_engine* e);
  * level: H9 [n_poses][9], dTr3 [n_poses][3]. All host pointers. */
 int hs_hessian_derivs_batch(hs_engine* e, int stream, int level, const float* poses_map, int n_poses,
                             const float* points, int n_points, float* H9, float* dTr3);
+/* Relocalisation-style multi-start matching (BASELINE configs[3]): MapRepMultiMap::matchData (MapRepMultiMap.h:116-132) of ONE
+ * scan (points [n_points][2], level-0 cells) against ONE stream's maps from n_hyp world pose hints [n_hyp][3] at once.
+ * The stream's state is not touched (no pose, no coarse containers, no integration). poses_out [n_hyp][3], cov_out
+ * [n_hyp][9] (the last level-0 Hessian, what getLastScanMatchCovariance would return); either may be NULL. Host pointers. */
+int hs_match_hypotheses(hs_engine* e, int stream, const float* points, int n_points, const float* pose_hints, int n_hyp,
+                        float* poses_out, float* cov_out);
 /* MapRepMultiMap::matchData only (HSL/slam_main/MapRepMultiMap.h:116-132): no gate, no integration,
  * last scan-match pose/covariance are updated like update() would. Host pointers. */
 int hs_match_batch(hs_engine* e, int n, const int32_t* stream_ids, const float* points, const int32_t* counts,

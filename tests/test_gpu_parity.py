@@ -181,3 +181,44 @@ def test_long_closed_loop_64_streams_1000_scans(hs, oracle):
         assert err.max() < 0.15, err.max()
     for p in procs:
         p.close()
+
+
+def test_multi_start_match_hypotheses(hs, oracle):
+    """hs_match_hypotheses (BASELINE configs[3], relocalisation-style multi-start match): the full coarse-to-fine matchData of
+    one scan from 512 pose hints against one stream's maps equals the reference's per-level ScanMatcher::matchData chained
+    coarse to fine (MapRepMultiMap.h:116-132), bit for bit, and leaves the stream's state untouched."""
+    n_scans = 60
+    sc, ranges, pts, cnt, truth = make_streams(hs, 2, n_scans + 1, seed0=2718)
+    cpu = cpu_streams(oracle, 1, dist=0.0, ang=0.0, free=0.4, occ=0.9)[0]
+    with hs.Engine(n_streams=2, max_points=360) as eng:
+        configure(eng, dist=0.0, ang=0.0, free=0.4, occ=0.9)
+        pose = None
+        for k in range(n_scans):
+            out, _ = eng.update_batch(pts[k], cnt[k])
+            pose = cpu.update(pts[k, 1], cnt[k, 1], hint=cpu.pose())
+        assert np.array_equal(bits(out[1]), bits(pose))
+        rng = np.random.default_rng(9)
+        n_hyp = 512
+        hints = (pose[None, :] + rng.uniform(-1, 1, (n_hyp, 3)) * np.array([0.3, 0.3, 0.15])).astype(np.float32)
+        scan = pts[n_scans, 1, :cnt[n_scans, 1]]
+        before = (eng.poses().copy(), eng.covariances().copy(), eng.download_level(1, 0).copy(), eng.update_index(1, 0))
+        got, gcov = eng.match_hypotheses(1, scan, hints)
+        after = (eng.poses(), eng.covariances(), eng.download_level(1, 0), eng.update_index(1, 0))
+        assert np.array_equal(bits(before[0]), bits(after[0])) and np.array_equal(bits(before[1]), bits(after[1]))
+        assert np.array_equal(before[2], after[2]) and before[3] == after[3]
+        n_ok = 0
+        for i in range(n_hyp):
+            p, c = hints[i], None
+            for level in (2, 1, 0):
+                p, c = cpu.match_level(level, p, scan * np.float32(1.0 / (1 << level)), 5 if level == 0 else 3)
+            if np.isfinite(p).all():
+                assert np.array_equal(bits(got[i]), bits(p)), i
+                assert np.array_equal(bits(gcov[i]), bits(c)), i
+                n_ok += 1
+        assert n_ok > n_hyp * 0.9
+        # the hypotheses near the true pose converge onto the matcher's own answer for that scan
+        ref_pose = cpu.update(pts[n_scans, 1], cnt[n_scans, 1], hint=cpu.pose())
+        near = np.linalg.norm(hints[:, :2] - pose[None, :2], axis=1) < 0.05
+        near &= np.abs(hints[:, 2] - pose[2]) < 0.03
+        assert near.sum() >= 1 and np.abs(got[near, :2] - ref_pose[None, :2]).max() < 0.02
+    cpu.close()

@@ -64,6 +64,17 @@ def hypotheses():
             dt = (time.perf_counter() - t0) / R
             print(json.dumps({"config": "configs[3]: 4096 pose hypotheses x %d points, level 0, host call incl. H2D/D2H" % len(p), "strict": strict,
                               "ms_per_call": dt * 1e3, "hypotheses_per_s": n / dt, "algorithmic_GBps": n * len(p) * 16 / dt / 1e9}))
+        # full coarse-to-fine multi-start match (14 evaluations per hypothesis), state untouched
+        eng.set_strict_summation(1)
+        hints = pose[0][None, :] + rng.uniform(-1, 1, (n, 3)).astype(np.float32) * np.array([1.0, 1.0, 0.5], np.float32)
+        for _ in range(3):
+            eng.match_hypotheses(0, p, hints)
+        t0 = time.perf_counter()
+        for _ in range(R):
+            got, cov = eng.match_hypotheses(0, p, hints)
+        dt = (time.perf_counter() - t0) / R
+        print(json.dumps({"config": "configs[3] full match: 4096 pose hypotheses x %d points, 3 levels (14 evaluations each), host call incl. H2D/D2H" % len(p),
+                          "ms_per_call": dt * 1e3, "hypotheses_per_s": n / dt, "evaluations_per_s": 14 * n / dt}))
 
 hypotheses()
 hires()

@@ -120,6 +120,7 @@ def lib():
         "hs_get_last_map_update_poses": (_I, [_P, _I, _I, _P]), "hs_device_pose_ptr": (_P, [_P]),
         "hs_hessian_derivs_batch": (_I, [_P, _I, _I, _P, _I, _P, _I, _P, _P]),
         "hs_match_batch": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _P]),
+        "hs_match_hypotheses": (_I, [_P, _I, _P, _I, _P, _I, _P, _P]),
         "hs_raycast_batch": (_I, [_P, _I, _P, _P, _P, _P, _P]),
         "hs_download_level": (_I, [_P, _I, _I, _P]), "hs_upload_level": (_I, [_P, _I, _I, _P]),
         "hs_get_update_index": (_I, [_P, _I, _I, _P]), "hs_classify_level": (_I, [_P, _I, _I, _P]),
@@ -344,6 +345,17 @@ class Engine:
         cov = np.empty((n, 9), np.float32)
         _check(lib().hs_match_batch(self._h, n, _ptr(ids), points.ctypes.data, counts.ctypes.data, _ptr(origos),
                                     _ptr(pose_hints), poses.ctypes.data, cov.ctypes.data), "hs_match_batch")
+        return poses, cov.reshape(n, 3, 3)
+
+    def match_hypotheses(self, stream, points, pose_hints):
+        """Multi-start matchData of one scan against one stream's maps: (poses [n][3], cov [n][3][3]); no state is touched."""
+        points = _arr(points, np.float32).reshape(-1, 2)
+        pose_hints = _arr(pose_hints, np.float32).reshape(-1, 3)
+        n = pose_hints.shape[0]
+        poses = np.empty((n, 3), np.float32)
+        cov = np.empty((n, 9), np.float32)
+        _check(lib().hs_match_hypotheses(self._h, stream, points.ctypes.data, points.shape[0], pose_hints.ctypes.data, n,
+                                         poses.ctypes.data, cov.ctypes.data), "hs_match_hypotheses")
         return poses, cov.reshape(n, 3, 3)
 
     def raycast_batch(self, points, counts, poses_world, origos=None, stream_ids=None):

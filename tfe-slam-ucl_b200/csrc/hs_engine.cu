@@ -952,6 +952,44 @@ int hs_hessian_derivs_batch(hs_engine* e, int stream, int level, const float* po
   return HS_OK;
 }
 
+// Relocalisation-style multi-start matching (BASELINE configs[3]): MapRepMultiMap::matchData (HSL/slam_main/MapRepMultiMap.h:116-132)
+// of ONE scan against ONE stream's maps from n_hyp different pose hints at once. Nothing of the stream's state is touched
+// (no pose, no coarse containers, no integration). poses_out [n_hyp][3] (world), cov_out [n_hyp][9] (the last level-0 Hessian,
+// as getLastScanMatchCovariance would return); either may be NULL.
+int hs_match_hypotheses(hs_engine* e, int stream, const float* points, int n_points, const float* pose_hints, int n_hyp,
+                        float* poses_out, float* cov_out) {
+  if (!e || stream < 0 || stream >= e->P.n_streams || n_points < 0 || n_points > e->P.max_points || n_hyp < 0) return HS_ERR_INVALID_ARG;
+  if (n_hyp == 0) return HS_OK;
+  if (!pose_hints || (!points && n_points > 0)) return HS_ERR_INVALID_ARG;
+  HS_CK(cudaSetDevice(e->device));
+  auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t b_pts = (size_t)e->P.max_points * 2 * sizeof(float), b_h = (size_t)n_hyp * 3 * sizeof(float), b_c = (size_t)n_hyp * 9 * sizeof(float);
+  const size_t o_cnt = align(b_pts), o_hint = o_cnt + 256, o_pose = o_hint + align(b_h), o_cov = o_pose + align(b_h);
+  int st = ensure_scratch(e, o_cov + b_c);
+  if (st != HS_OK) return st;
+  char* base = (char*)e->d_scratch;
+  const int32_t cnt = n_points;
+  if (n_points > 0) HS_CK(cudaMemcpyAsync(base, points, (size_t)n_points * 2 * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  HS_CK(cudaMemcpyAsync(base + o_cnt, &cnt, sizeof(cnt), cudaMemcpyHostToDevice, e->stream));
+  HS_CK(cudaMemcpyAsync(base + o_hint, pose_hints, b_h, cudaMemcpyHostToDevice, e->stream));
+  HS_CK(cudaMemsetAsync(base + o_cov, 0, b_c, e->stream));   // an empty scan leaves the covariance untouched (ScanMatcher.h:189)
+  e->h2d_bytes += (size_t)n_points * 8 + 4 + b_h;
+  const int saved_stream = e->P.hyp_stream;
+  e->P.hyp_pose = (float*)(base + o_pose);
+  e->P.hyp_cov = (float*)(base + o_cov);
+  e->P.hyp_stream = stream;
+  st = run_update_device(e, n_hyp, nullptr, (const float*)base, (const int32_t*)(base + o_cnt), nullptr, (const float*)(base + o_hint), nullptr, 1);
+  e->P.hyp_pose = nullptr;
+  e->P.hyp_cov = nullptr;
+  e->P.hyp_stream = saved_stream;
+  e->updates -= (uint64_t)n_hyp;   // hypotheses are not stream updates
+  if (st != HS_OK) return st;
+  if (poses_out) { HS_CK(cudaMemcpyAsync(poses_out, base + o_pose, b_h, cudaMemcpyDeviceToHost, e->stream)); e->d2h_bytes += b_h; }
+  if (cov_out) { HS_CK(cudaMemcpyAsync(cov_out, base + o_cov, b_c, cudaMemcpyDeviceToHost, e->stream)); e->d2h_bytes += b_c; }
+  HS_CK(cudaStreamSynchronize(e->stream));
+  return HS_OK;
+}
+
 int hs_raycast_batch(hs_engine* e, int n, const int32_t* stream_ids, const float* points, const int32_t* counts,
                      const float* origos, const float* poses_world) {
   int st = check_batch(e, n);

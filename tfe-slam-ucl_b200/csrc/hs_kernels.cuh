@@ -50,6 +50,11 @@ struct HsParams {
   float2* stage_pts;                // matcher: non-NULL = `points` is pinned HOST memory read over PCIe; each CTA copies its scan here
                                     // (device, [slot][max_points]) in one pass and everything else reads the copy
   int32_t* stage_cnt;               // ... and its point count here ([slot]); NULL = `counts` is already device memory
+  // multi-start matching (hs_match_hypotheses): non-NULL = every slot matches the SAME scan (slot 0's points) against the
+  // maps of stream `hyp_stream` from its own hint, touches no stream state, and writes pose / covariance here ([slot][3], [slot][9])
+  float* hyp_pose;
+  float* hyp_cov;
+  int hyp_stream;
   float* host_pose_out;             // non-NULL: the caller's pinned poses_out [slot][3]; the matcher's tail writes the pose there too
   int tail_slots;                   // k_raycast: the last `tail_slots` slots of a launch are dispatched level-major
   int slot0;                        // first slot of this launch (a host batch may be cut into chunks that run on several CUDA streams)
@@ -487,10 +492,11 @@ __global__ void __launch_bounds__(HS_MATCH_THREADS, (PPT > 0 && PPT <= 3) ? 7 : 
   // serial warps of the CTAs sharing an SM sit on different SM sub-partitions (warp w issues from scheduler w mod 4)
   const int sw = blockIdx.x & ((blockDim.x >> 5) - 1);
   const bool serial = (tid >> 5) == sw, leader = tid == (sw << 5);
-  const int s = hs_slot_stream(stream_ids, slot);
-  int n = counts[slot];
+  const bool hyp = P.hyp_pose != nullptr;
+  const int s = hyp ? P.hyp_stream : hs_slot_stream(stream_ids, slot);
+  int n = counts[hyp ? 0 : slot];
   n = n < 0 ? 0 : (n > P.max_points ? P.max_points : n);
-  const float2* pts = points + (size_t)slot * P.max_points;
+  const float2* pts = points + (hyp ? (size_t)0 : (size_t)slot * P.max_points);
   if (P.stage_pts) {   // zero-copy input: fetch this scan from the caller's pinned host buffer once
     if (P.stage_cnt && tid == 0) P.stage_cnt[slot] = n;
     float2* stg = P.stage_pts + (size_t)slot * P.max_points;
@@ -509,8 +515,8 @@ __global__ void __launch_bounds__(HS_MATCH_THREADS, (PPT > 0 && PPT <= 3) ? 7 : 
     // dataContainers[level-1].setFrom(dataContainer, 2^-level) (MapRepMultiMap.h:127): keep the level-0
     // points of the last matched scan; the power-of-two factor is applied (exactly) where they are used.
     float2* cp = reinterpret_cast<float2*>(P.coarse_pts) + (size_t)s * P.max_points;
-    for (int i = tid; i < n; i += blockDim.x) cp[i] = pts[i];
-    if (tid == 0) {
+    if (!hyp) for (int i = tid; i < n; i += blockDim.x) cp[i] = pts[i];
+    if (tid == 0 && !hyp) {
       P.coarse_cnt[s] = n;
       float2 o = origos ? origos[slot] : make_float2(0.f, 0.f);
       P.coarse_origo[2 * s] = o.x;
@@ -559,7 +565,7 @@ __global__ void __launch_bounds__(HS_MATCH_THREADS, (PPT > 0 && PPT <= 3) ? 7 : 
         }
       }
       if (leader) {
-        float* c = P.cov + 9 * (size_t)s;  // covMatrix = H of the last evaluation (ScanMatcher.h:184)
+        float* c = hyp ? P.hyp_cov + 9 * (size_t)slot : P.cov + 9 * (size_t)s;  // covMatrix = H of the last evaluation (ScanMatcher.h:184)
         c[0] = a.h00; c[1] = a.h01; c[2] = a.h02;
         c[3] = a.h01; c[4] = a.h11; c[5] = a.h12;
         c[6] = a.h02; c[7] = a.h12; c[8] = a.h22;
@@ -568,7 +574,10 @@ __global__ void __launch_bounds__(HS_MATCH_THREADS, (PPT > 0 && PPT <= 3) ? 7 : 
       mt.end();
     }
   }
-  if (leader) hs_match_tail(P, slot, s, wx, wy, wth, mwm, mode);
+  if (leader) {
+    if (hyp) { P.hyp_pose[3 * slot] = wx; P.hyp_pose[3 * slot + 1] = wy; P.hyp_pose[3 * slot + 2] = wth; }
+    else hs_match_tail(P, slot, s, wx, wy, wth, mwm, mode);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -729,10 +738,11 @@ __global__ void __launch_bounds__(HS_MATCH_THREADS) k_match2(HsParams P, int n_s
   // serial warps of the CTAs sharing an SM sit on different SM sub-partitions (warp w issues from scheduler w mod 4)
   const int sw = blockIdx.x & ((blockDim.x >> 5) - 1);
   const bool serial = (tid >> 5) == sw, leader = tid == (sw << 5);
-  const int s = hs_slot_stream(stream_ids, slot);
-  int n = counts[slot];
+  const bool hyp = P.hyp_pose != nullptr;
+  const int s = hyp ? P.hyp_stream : hs_slot_stream(stream_ids, slot);
+  int n = counts[hyp ? 0 : slot];
   n = n < 0 ? 0 : (n > P.max_points ? P.max_points : n);
-  const float2* pts = points + (size_t)slot * P.max_points;
+  const float2* pts = points + (hyp ? (size_t)0 : (size_t)slot * P.max_points);
   if (P.stage_pts) {   // zero-copy input: fetch this scan from the caller's pinned host buffer once
     if (P.stage_cnt && tid == 0) P.stage_cnt[slot] = n;
     float2* stg = P.stage_pts + (size_t)slot * P.max_points;
@@ -751,12 +761,14 @@ __global__ void __launch_bounds__(HS_MATCH_THREADS) k_match2(HsParams P, int n_s
     // dataContainers[level-1].setFrom(dataContainer, 2^-level) (MapRepMultiMap.h:127): keep the level-0
     // points of the last matched scan; the power-of-two factor is applied (exactly) where they are used.
     float2* cp = reinterpret_cast<float2*>(P.coarse_pts) + (size_t)s * P.max_points;
-    for (int i = tid; i < n; i += blockDim.x) { const float2 p = pts[i]; cp[i] = p; spts[i] = p; }
+    for (int i = tid; i < n; i += blockDim.x) { const float2 p = pts[i]; if (!hyp) cp[i] = p; spts[i] = p; }
     if (tid == 0) {
-      P.coarse_cnt[s] = n;
-      float2 o = origos ? origos[slot] : make_float2(0.f, 0.f);
-      P.coarse_origo[2 * s] = o.x;
-      P.coarse_origo[2 * s + 1] = o.y;
+      if (!hyp) {
+        P.coarse_cnt[s] = n;
+        float2 o = origos ? origos[slot] : make_float2(0.f, 0.f);
+        P.coarse_origo[2 * s] = o.x;
+        P.coarse_origo[2 * s + 1] = o.y;
+      }
       s_nmiss = 0;
     }
     if (n != 0) {
@@ -792,7 +804,7 @@ __global__ void __launch_bounds__(HS_MATCH_THREADS) k_match2(HsParams P, int n_s
         }
       }
       if (leader) {
-        float* c = P.cov + 9 * (size_t)s;  // covMatrix = H of the last evaluation (ScanMatcher.h:184)
+        float* c = hyp ? P.hyp_cov + 9 * (size_t)slot : P.cov + 9 * (size_t)s;  // covMatrix = H of the last evaluation (ScanMatcher.h:184)
         c[0] = a.h00; c[1] = a.h01; c[2] = a.h02;
         c[3] = a.h01; c[4] = a.h11; c[5] = a.h12;
         c[6] = a.h02; c[7] = a.h12; c[8] = a.h22;
@@ -801,7 +813,10 @@ __global__ void __launch_bounds__(HS_MATCH_THREADS) k_match2(HsParams P, int n_s
       mt.end();
     }
   }
-  if (leader) hs_match_tail(P, slot, s, wx, wy, wth, mwm, mode);
+  if (leader) {
+    if (hyp) { P.hyp_pose[3 * slot] = wx; P.hyp_pose[3 * slot + 1] = wy; P.hyp_pose[3 * slot + 2] = wth; }
+    else hs_match_tail(P, slot, s, wx, wy, wth, mwm, mode);
+  }
 }
 
 // k_force_integrate: teacher-forced integration set-up (hs_raycast_batch): refresh the coarse containers from
