@@ -14,7 +14,9 @@ ROS node's 0.4 / 0.9.
     value  : inputs (DataContainer points of all steps) already resident in HBM, hs_update_batch_device,
              timed with CUDA events on the launching stream.
     e2e    : hs_update_batch (the reference-facing C-ABI call) with pinned HOST buffers; the H2D copy of
-             each step's points/counts and the D2H read of the matched poses are inside the timed region.
+             each step's points/counts and the D2H read of the matched poses are inside the timed region. Each call
+             returns when its poses are in host memory; its map integration finishes on the engine's stream (the next call
+             is ordered behind it) and the timed region ends with a device synchronisation, so all K integrations are inside.
     roofline    : the dominant kernel's algorithmic bytes / its CUDA-event time, against MEASURED_PEAKS.json.
     cpu_baseline: the CPU reference (oracle/_ref if built, else the C restatement) on a bounded sample.
 
@@ -273,7 +275,7 @@ def main():
     t0 = time.perf_counter()
     for k in range(W, W + K):
         run_host(k)   # returns when this step's poses are valid in host memory
-    torch.cuda.synchronize()
+    torch.cuda.synchronize()   # ... and the last step's map integration has finished
     e2e_s = time.perf_counter() - t0
     pose_checksum = float(h_pose.sum())
 

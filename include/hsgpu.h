@@ -100,7 +100,12 @@ const char* hs_status_string(int status);
  *   map_without_matching [n] bool flags, or NULL for false
  *   poses_out            [n][3] getLastScanMatchPose() after the update, or NULL
  *   cov_out              [n][9] getLastScanMatchCovariance() (the last level-0 Hessian), or NULL
- * Host variant: copies inputs H2D, runs, copies outputs D2H and returns when they are valid. */
+ * Host variant: copies inputs H2D, runs, copies outputs D2H and returns when they are valid.
+ * Deferred integration: when points, counts and poses_out are pinned host memory (cudaHostAlloc / cudaHostRegister),
+ * stream_ids and cov_out are NULL, the call returns as soon as the poses are in poses_out; this batch's updateByScan keeps
+ * running on the engine's stream, every later call on the engine (another update, a map or pose read, hs_synchronize) is
+ * ordered behind it, and the input buffers may be reused on return. The next call's points are then fetched while that
+ * integration runs. HSGPU_E2E_DEFER=0 restores "returns after the integration". */
 int hs_update_batch(hs_engine* e, int n, const int32_t* stream_ids, const float* points, const int32_t* counts,
                     const float* origos, const float* pose_hints, const uint8_t* map_without_matching,
                     float* poses_out, float* cov_out);

@@ -311,8 +311,10 @@ def test_offpath_members_on_random_maps(hs, oracle):
 def test_pinned_host_batches_zero_copy_and_chunked_are_identical(hs, monkeypatch):
     """With pinned host buffers hs_update_batch lets the matcher read the scans straight from host memory (zero-copy, the
     default) or, with HSGPU_E2E_ZERO_COPY=0, cuts the batch into chunks on several CUDA streams (copy of chunk c+1 under the
-    kernels of chunk c). Results must not depend on the transport: zero-copy, 1, 2, 3 and 4 chunks, with and without
-    stream_ids, all bit-identical."""
+    kernels of chunk c), or (HSGPU_E2E_DEFER=1/2, the default is 1) returns as soon as the poses are in the caller's buffer
+    and lets the map integration run on while the next call's points are prefetched. Results must not depend on the
+    transport: zero-copy, 1, 2, 3 and 4 chunks, deferred with a DMA or a copy-kernel prefetch, with and without stream_ids,
+    all bit-identical -- and the poses must be valid the moment the call returns."""
     import torch
     n, n_scans = 300, 5
     sc, ranges, pts, cnt, truth = make_streams(hs, n, n_scans, seed0=9000)
@@ -320,18 +322,21 @@ def test_pinned_host_batches_zero_copy_and_chunked_are_identical(hs, monkeypatch
     h_cnt = torch.from_numpy(cnt).pin_memory()
     ids = torch.from_numpy(np.random.default_rng(3).permutation(n).astype(np.int32)).pin_memory()
     results = []
-    for chunks in ("1", "2", "3", "4", "zero-copy"):
-        monkeypatch.setenv("HSGPU_E2E_ZERO_COPY", "1" if chunks == "zero-copy" else "0")
-        monkeypatch.setenv("HSGPU_E2E_CHUNKS", "2" if chunks == "zero-copy" else chunks)
+    for chunks in ("1", "2", "3", "4", "zero-copy", "defer-1", "defer-2"):
+        monkeypatch.setenv("HSGPU_E2E_ZERO_COPY", "0" if chunks.isdigit() else "1")
+        monkeypatch.setenv("HSGPU_E2E_CHUNKS", chunks if chunks.isdigit() else "2")
+        monkeypatch.setenv("HSGPU_E2E_DEFER", chunks[-1] if chunks.startswith("defer") else "0")
         for use_ids in (False, True):
             with hs.Engine(n_streams=n, max_points=360) as eng:
                 eng.set_update_factor_free(0.4); eng.set_update_factor_occupied(0.9)
                 eng.set_map_update_min_dist_diff(0.0); eng.set_map_update_min_angle_diff(0.0)
-                out = torch.empty((n_scans, n, 3), dtype=torch.float32).pin_memory()
+                out = torch.full((n_scans, n, 3), float("nan"), dtype=torch.float32).pin_memory()
+                at_return = []
                 for k in range(n_scans):
                     eng.update_batch_raw(n, h_pts[k].data_ptr(), h_cnt[k].data_ptr(), out[k].data_ptr(),
                                          ids_ptr=ids.data_ptr() if use_ids else None)
-                poses = out.numpy().copy()
+                    at_return.append(out[k].numpy().copy())   # no further synchronisation: valid when the call returns
+                poses = np.stack(at_return)
                 if use_ids:   # slot i updated stream ids[i]: bring back to stream order
                     inv = np.empty(n, np.int64); inv[ids.numpy()] = np.arange(n)
                     final = eng.poses()
@@ -514,3 +519,38 @@ def test_fuzz_random_scans_teacher_forced_and_matched(hs, oracle):
         for p in procs:
             p.close()
     assert n_checked >= 40, n_checked   # most of the 72 random streams give a finite match
+
+
+def test_pinned_ranges_entry_point_deferred_and_synchronous_identical(hs, monkeypatch):
+    """hs_update_batch_ranges with pinned buffers: the deferred-integration transport (returns after the match, ranges of the
+    next call prefetched by DMA) and the synchronous one give the same poses -- valid at return -- and the same maps as the
+    points entry point fed with the host conversion of the same ranges."""
+    import torch
+    n, n_scans = 200, 6
+    sc, ranges, pts, cnt, truth = make_streams(hs, n, n_scans, seed0=515)
+    ranges = ranges.copy()
+    ranges[np.random.default_rng(2).random(ranges.shape) < 0.2] = np.inf
+    pts, cnt = hs.scan_to_points_host(ranges, sc, 20.0)
+    h_rng = torch.from_numpy(ranges).pin_memory()
+    results = []
+    for defer in ("0", "1", "points"):
+        monkeypatch.setenv("HSGPU_E2E_DEFER", "0" if defer == "points" else defer)
+        with hs.Engine(n_streams=n, max_points=360) as eng:
+            eng.set_update_factor_free(0.4); eng.set_update_factor_occupied(0.9)
+            eng.set_map_update_min_dist_diff(0.0); eng.set_map_update_min_angle_diff(0.0)
+            eng.set_scan_geometry(sc.n_beams, sc.angle_min, sc.angle_increment, sc.range_min, sc.range_max)
+            out = torch.full((n_scans, n, 3), float("nan"), dtype=torch.float32).pin_memory()
+            at_return = []
+            for k in range(n_scans):
+                if defer == "points":
+                    o, _ = eng.update_batch(pts[k], cnt[k], want_cov=False)
+                    at_return.append(o.copy())
+                else:
+                    eng.update_batch_ranges_raw(n, h_rng[k].data_ptr(), out[k].data_ptr())
+                    at_return.append(out[k].numpy().copy())
+            maps = [eng.download_level(s, l) for s in (0, n - 1) for l in (0, 2)]
+            results.append((np.stack(at_return), eng.poses().copy(), [(m["logOddsVal"].copy(), m["updateIndex"].copy()) for m in maps]))
+    for r in results[:-1]:
+        assert np.array_equal(bits(r[0]), bits(results[-1][0])) and np.array_equal(bits(r[1]), bits(results[-1][1]))
+        for (a, ai), (b, bi) in zip(r[2], results[-1][2]):
+            assert np.array_equal(bits(a), bits(b)) and np.array_equal(ai, bi)

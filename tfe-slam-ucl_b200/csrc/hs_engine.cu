@@ -24,7 +24,8 @@ struct hs_engine {
   cudaStream_t own_stream;
   cudaStream_t stream;
   // host batches are cut into chunks whose host-to-device copies overlap the kernels of the previous chunk
-  int e2e_chunks, e2e_first_pct, e2e_zero_copy;
+  int e2e_chunks, e2e_first_pct, e2e_zero_copy, e2e_defer, sm_count = 148;
+  cudaEvent_t ev_match = nullptr;
   cudaStream_t aux_stream[HS_MAX_CHUNKS - 1];
   cudaEvent_t ev_fork, ev_join[HS_MAX_CHUNKS - 1];
   // staging (device) for the host-pointer entry points
@@ -38,7 +39,7 @@ struct hs_engine {
   float* d_out;      // [n_streams][9] gather scratch
   // pipelined submission (hs_submit_batch): two sets of input staging buffers filled by DMA on a copy stream while the
   // previous batch computes; allocated on first use
-  struct PipeBuf { float* points; int32_t* counts; float* origos; float* hints; uint8_t* flags; int32_t* ids; cudaEvent_t staged, consumed; };
+  struct PipeBuf { float* points; float* ranges; int32_t* counts; float* origos; float* hints; uint8_t* flags; int32_t* ids; cudaEvent_t staged, consumed; };
   PipeBuf pipe[2];
   cudaStream_t copy_stream;
   uint64_t submits;
@@ -197,6 +198,7 @@ int hs_create(const hs_config* cfg, hs_engine** out) {
   {
     int n_sm = 148;
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, cfg->device);
+    e->sm_count = n_sm;
     P.tail_slots = 2 * n_sm;   // measured on B200 (148 SMs): 0 -> 179 us, 148 -> 178, 296 -> 176, 444 -> 178.5, 600 -> 181
   }
   if (const char* ts = getenv("HSGPU_RAYCAST_TAIL_SLOTS")) P.tail_slots = atoi(ts) < 0 ? 0 : atoi(ts);
@@ -290,6 +292,8 @@ int hs_create(const hs_config* cfg, hs_engine** out) {
     e->e2e_first_pct = 100;
     e->e2e_zero_copy = 1;
     if (const char* z = getenv("HSGPU_E2E_ZERO_COPY")) e->e2e_zero_copy = atoi(z) != 0;
+    e->e2e_defer = 1;    // 0: the call returns after the map integration; 1/2: after the match (inputs prefetched by DMA / by a copy kernel)
+    if (const char* z = getenv("HSGPU_E2E_DEFER")) e->e2e_defer = atoi(z);
     if (const char* c = getenv("HSGPU_E2E_FIRST_PCT")) e->e2e_first_pct = atoi(c) < 5 ? 5 : (atoi(c) > 100 ? 100 : atoi(c));
     cudaError_t err = cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming);
     for (int c = 0; c < HS_MAX_CHUNKS - 1 && err == cudaSuccess; ++c) {
@@ -378,7 +382,7 @@ int hs_destroy(hs_engine* e) {
     if (p) cudaFree(p);
   if (e->copy_stream) { cudaStreamSynchronize(e->copy_stream); cudaStreamDestroy(e->copy_stream); }
   for (int b = 0; b < 2; ++b) {
-    void* pp[] = {e->pipe[b].points, e->pipe[b].counts, e->pipe[b].origos, e->pipe[b].hints, e->pipe[b].flags, e->pipe[b].ids};
+    void* pp[] = {e->pipe[b].points, e->pipe[b].ranges, e->pipe[b].counts, e->pipe[b].origos, e->pipe[b].hints, e->pipe[b].flags, e->pipe[b].ids};
     for (void* q : pp) if (q) cudaFree(q);
     if (e->pipe[b].staged) cudaEventDestroy(e->pipe[b].staged);
     if (e->pipe[b].consumed) cudaEventDestroy(e->pipe[b].consumed);
@@ -388,6 +392,7 @@ int hs_destroy(hs_engine* e) {
     if (e->ev_join[c]) cudaEventDestroy(e->ev_join[c]);
   }
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  if (e->ev_match) cudaEventDestroy(e->ev_match);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
   if (e->prof_events) {
     for (cudaEvent_t ev : *e->prof_events) cudaEventDestroy(ev);
@@ -483,7 +488,7 @@ static int check_batch(const hs_engine* e, int n) {
 static int run_update_device(hs_engine* e, int n, const int32_t* ids, const float* points, const int32_t* counts,
                              const float* origos, const float* hints, const uint8_t* flags, int mode,
                              cudaStream_t st = nullptr, int slot0 = 0, float* stage = nullptr, int32_t* stage_cnt = nullptr,
-                             float* host_pose_out = nullptr) {
+                             float* host_pose_out = nullptr, cudaEvent_t ev_matched = nullptr) {
   if (n == 0) return HS_OK;
   if (!st) st = e->stream;
   HsParams Pc = e->P;
@@ -527,6 +532,7 @@ static int run_update_device(hs_engine* e, int n, const int32_t* ids, const floa
     }
   }
   HS_LAUNCHED(e);
+  if (ev_matched) HS_CK(cudaEventRecord(ev_matched, st));
   if (mode == 0) {
     {
       ProfScope ps(e, HS_K_RAYCAST);
@@ -586,6 +592,23 @@ int hs_update_batch_device(hs_engine* e, int n, const int32_t* stream_ids, const
   return run_update_device(e, n, stream_ids, points, counts, origos, pose_hints, map_without_matching, 0);
 }
 
+static int pipe_init(hs_engine* e);
+
+// Copies `n16` 16-byte words of pinned host memory (mapped, read over PCIe) into device memory. One warp per CTA and at
+// most 32 registers per thread, so that a CTA fits into the registers k_raycast leaves free on an SM (3 x 384 threads x 56
+// registers of 64 K): launched on a high-priority stream it runs underneath the previous batch's ray-cast.
+__global__ void __launch_bounds__(64, 32) k_prefetch_host(const float4* __restrict__ src, float4* __restrict__ dst, unsigned n16,
+                                                          const int32_t* __restrict__ cnt_src, int32_t* __restrict__ cnt_dst, int n) {
+  const unsigned stride = gridDim.x * blockDim.x;
+  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < (unsigned)n) cnt_dst[i] = cnt_src[i];
+  for (; i + 3 * stride < n16; i += 4 * stride) {
+    const float4 a = __ldcs(src + i), b = __ldcs(src + i + stride), c = __ldcs(src + i + 2 * stride), d = __ldcs(src + i + 3 * stride);
+    dst[i] = a; dst[i + stride] = b; dst[i + 2 * stride] = c; dst[i + 3 * stride] = d;
+  }
+  for (; i < n16; i += stride) dst[i] = __ldcs(src + i);
+}
+
 static int update_host(hs_engine* e, int n, const int32_t* ids, const float* points, const int32_t* counts, const float* origos,
                        const float* hints, const uint8_t* flags, float* poses_out, float* cov_out, int mode) {
   int st = check_batch(e, n);
@@ -609,6 +632,36 @@ static int update_host(hs_engine* e, int n, const int32_t* ids, const float* poi
   const int32_t* m_counts = (m_points && e->e2e_zero_copy) ? (const int32_t*)mapped(counts) : nullptr;
   // poses_out pinned: the matcher writes the poses straight into it (no D2H copy behind the last kernel)
   float* m_poses = (m_points && e->e2e_zero_copy && poses_out && !ids) ? (float*)mapped(poses_out) : nullptr;
+  if (mode == 0 && e->e2e_defer && m_points && m_counts && m_poses && !cov_out) {
+    // Deferred integration: the call returns as soon as the poses are in the caller's buffer; the map integration of this
+    // batch keeps running on the engine's stream, and every later call on the engine is ordered behind it. The next
+    // call's points are then fetched into a second staging set WHILE that ray-cast runs (copy stream), so that a caller
+    // looping over update() pays for the PCIe transfer only once, on the first call.
+    if ((st = pipe_init(e)) != HS_OK) return st;
+    if (!e->ev_match) HS_CK(cudaEventCreateWithFlags(&e->ev_match, cudaEventDisableTiming));
+    hs_engine::PipeBuf& B = e->pipe[e->submits & 1];
+    cudaStream_t cp = e->copy_stream;
+    HS_CK(cudaStreamWaitEvent(cp, B.consumed, 0));
+    if (e->e2e_defer == 2 && (n * row) % 4 == 0) {
+      k_prefetch_host<<<2 * e->sm_count, 32, 0, cp>>>((const float4*)m_points, (float4*)B.points, (unsigned)(n * row / 4), m_counts, B.counts, n);
+      HS_LAUNCHED(e);
+    } else {
+      HS_CK(cudaMemcpyAsync(B.points, points, pbytes, cudaMemcpyHostToDevice, cp));
+      HS_CK(cudaMemcpyAsync(B.counts, counts, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, cp));
+    }
+    HS_CK(cudaEventRecord(B.staged, cp));
+    if ((st = stage_common(e, n, nullptr, nullptr, origos, hints, flags)) != HS_OK) return st;
+    HS_CK(cudaStreamWaitEvent(e->stream, B.staged, 0));
+    st = run_update_device(e, n, nullptr, B.points, B.counts, origos ? e->d_origos : nullptr, hints ? e->d_hints : nullptr,
+                           flags ? e->d_flags : nullptr, 0, e->stream, 0, nullptr, nullptr, m_poses, e->ev_match);
+    if (st != HS_OK) return st;
+    HS_CK(cudaEventRecord(B.consumed, e->stream));
+    e->submits++;
+    e->h2d_bytes += pbytes + (size_t)n * sizeof(int32_t);
+    e->d2h_bytes += (size_t)n * 3 * sizeof(float);
+    HS_CK(cudaEventSynchronize(e->ev_match));
+    return HS_OK;
+  }
   if ((st = stage_common(e, n, ids, m_counts ? nullptr : counts, origos, hints, flags)) != HS_OK) return st;
   // The points are the bulk of the input (2.9 KB per 360-beam scan).
   // Pinned host memory is mapped into the device's address space (UVA): the matcher CTAs then fetch their scans straight
@@ -691,10 +744,13 @@ int hs_match_batch(hs_engine* e, int n, const int32_t* stream_ids, const float* 
 static int pipe_init(hs_engine* e) {
   if (e->copy_stream) return HS_OK;
   const size_t ns = (size_t)e->P.n_streams, mp = (size_t)e->P.max_points;
-  HS_CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+  int prio_lo = 0, prio_hi = 0;
+  HS_CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  HS_CK(cudaStreamCreateWithPriority(&e->copy_stream, cudaStreamNonBlocking, prio_hi));
   for (int b = 0; b < 2; ++b) {
     hs_engine::PipeBuf& B = e->pipe[b];
     HS_CK(cudaMalloc((void**)&B.points, ns * mp * 2 * sizeof(float)));
+    HS_CK(cudaMalloc((void**)&B.ranges, ns * mp * sizeof(float)));   // n_beams <= max_points
     HS_CK(cudaMalloc((void**)&B.counts, ns * sizeof(int32_t)));
     HS_CK(cudaMalloc((void**)&B.origos, ns * 2 * sizeof(float)));
     HS_CK(cudaMalloc((void**)&B.hints, ns * 3 * sizeof(float)));
@@ -817,6 +873,37 @@ int hs_update_batch_ranges(hs_engine* e, int n, const int32_t* stream_ids, const
   if ((st = check_ids(e, n, stream_ids)) != HS_OK) return st;
   HS_CK(cudaSetDevice(e->device));
   size_t rbytes = (size_t)n * e->n_beams * sizeof(float);
+  if (e->e2e_defer && e->e2e_zero_copy && !stream_ids && !cov_out && poses_out) {   // deferred integration, see update_host
+    cudaPointerAttributes ar, ap;
+    const bool pinned = cudaPointerGetAttributes(&ar, ranges) == cudaSuccess && ar.type == cudaMemoryTypeHost && ar.devicePointer &&
+                        cudaPointerGetAttributes(&ap, poses_out) == cudaSuccess && ap.type == cudaMemoryTypeHost && ap.devicePointer;
+    cudaGetLastError();
+    if (pinned) {
+      if ((st = pipe_init(e)) != HS_OK) return st;
+      if (!e->ev_match) HS_CK(cudaEventCreateWithFlags(&e->ev_match, cudaEventDisableTiming));
+      hs_engine::PipeBuf& B = e->pipe[e->submits & 1];
+      HS_CK(cudaStreamWaitEvent(e->copy_stream, B.consumed, 0));
+      HS_CK(cudaMemcpyAsync(B.ranges, ranges, rbytes, cudaMemcpyHostToDevice, e->copy_stream));
+      HS_CK(cudaEventRecord(B.staged, e->copy_stream));
+      if ((st = stage_common(e, n, nullptr, nullptr, nullptr, pose_hints, map_without_matching)) != HS_OK) return st;
+      HS_CK(cudaStreamWaitEvent(e->stream, B.staged, 0));
+      {
+        ProfScope ps(e, HS_K_SCAN_TO_POINTS);
+        k_scan_to_points<<<warp_grid(n, 128), 128, 0, e->stream>>>(B.ranges, n, e->n_beams, e->d_beam_cs, e->range_min, e->max_range_for_container,
+                                                                   e->P.lv[0].scale, e->P.max_points, (float2*)B.points, B.counts);
+      }
+      HS_LAUNCHED(e);
+      st = run_update_device(e, n, nullptr, B.points, B.counts, nullptr, pose_hints ? e->d_hints : nullptr,
+                             map_without_matching ? e->d_flags : nullptr, 0, e->stream, 0, nullptr, nullptr, (float*)ap.devicePointer, e->ev_match);
+      if (st != HS_OK) return st;
+      HS_CK(cudaEventRecord(B.consumed, e->stream));
+      e->submits++;
+      e->h2d_bytes += rbytes;
+      e->d2h_bytes += (size_t)n * 3 * sizeof(float);
+      HS_CK(cudaEventSynchronize(e->ev_match));
+      return HS_OK;
+    }
+  }
   const float* d_src = e->d_ranges;
   {   // pinned host memory: k_scan_to_points reads the ranges straight from the caller's buffer (zero-copy, see update_host)
     cudaPointerAttributes attr;
