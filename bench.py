@@ -37,6 +37,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "scans matched+integrated/sec (360-beam, 3-level 1024^2 grid)"
 UNIT = "scans/s"
+PROF_EVERY = 4   # per-kernel CUDA events around every 4th timed step (event pairs keep consecutive kernels from overlapping)
 NODE_FACTORS = (0.4, 0.9)  # HectorMappingRos.cpp:72-73
 E_EVALS = 14               # 4*(L-1)+6 evaluations per scan, L=3
 FALLBACK_HBM_GBS = 6650.0  # B200_PROFILING.md fallback
@@ -234,7 +235,7 @@ def main():
         run_device(k)
     barrier()
     st0 = eng.stats()
-    eng.profile_enable(True)
+    eng.profile_enable(PROF_EVERY)   # CUDA events around the kernels of every PROF_EVERY-th timed step
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.3)
@@ -339,6 +340,7 @@ def main():
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                 "traffic_source": traffic_src,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": per[dom][0], "avg_launch_ms": per[dom][1],
+                "kernel_timing": "CUDA events on the launching stream around the kernels of every %d-th timed step (%d launches of each kernel)" % (PROF_EVERY, kr["launches"]),
                 "kernels": {n: {"avg_launch_ms": per[n][1], "algorithmic_bytes_per_launch": per[n][0],
                                 "achieved_gbs": per[n][0] / (per[n][1] * 1e-3) / 1e9 if per[n][1] > 0 else None,
                                 "share_of_step": per[n][1] / (ms_total / K)} for n in per},

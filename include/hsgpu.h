@@ -264,6 +264,8 @@ typedef struct {
   double ms[3];
   uint64_t launches[3];
 } hs_kernel_times;
+/* on: 0 = off, 1 = around every kernel, n > 1 = around the kernels of every n-th update only (the event pairs keep
+ * consecutive kernels from overlapping their launch and drain, ~6 us per pair, so a sampled measurement perturbs less). */
 int hs_profile_enable(hs_engine* e, int on);
 /* Waits for the stream, sums the elapsed time per kernel since the last collect/enable, and clears the log. */
 int hs_profile_collect(hs_engine* e, hs_kernel_times* out);

@@ -25,6 +25,7 @@ struct hs_engine {
   cudaStream_t stream;
   // host batches are cut into chunks whose host-to-device copies overlap the kernels of the previous chunk
   int e2e_chunks, e2e_first_pct, e2e_zero_copy, e2e_defer, sm_count = 148;
+  int prof_every = 1; unsigned prof_tick = 0;   // kernel events around every prof_every-th update only
   cudaEvent_t ev_match = nullptr;
   cudaStream_t aux_stream[HS_MAX_CHUNKS - 1];
   cudaEvent_t ev_fork, ev_join[HS_MAX_CHUNKS - 1];
@@ -503,6 +504,13 @@ static int run_update_device(hs_engine* e, int n, const int32_t* ids, const floa
     StreamSwap(hs_engine* en, cudaStream_t s) : e(en), saved(en->stream) { e->stream = s; }
     ~StreamSwap() { e->stream = saved; }
   } swap(e, st);
+  struct ProfGate {   // sampled kernel timing: the events of the other updates stay out of the stream
+    hs_engine* e; int saved;
+    explicit ProfGate(hs_engine* en) : e(en), saved(en->profiling) {
+      if (saved && e->prof_every > 1 && (e->prof_tick++ % (unsigned)e->prof_every) != 0) e->profiling = 0;
+    }
+    ~ProfGate() { e->profiling = saved; }
+  } gate(e);
   {
     ProfScope ps(e, HS_K_MATCH);
     const int threads = HS_MATCH_THREADS;
@@ -1390,6 +1398,8 @@ int hs_profile_enable(hs_engine* e, int on) {
   HS_CK(cudaSetDevice(e->device));
   HS_CK(cudaStreamSynchronize(e->stream));
   e->profiling = on ? 1 : 0;
+  e->prof_every = on > 1 ? on : 1;
+  e->prof_tick = 0;
   e->prof_used = 0;
   e->prof_ids->clear();
   return HS_OK;
