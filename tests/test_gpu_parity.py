@@ -141,7 +141,7 @@ def test_both_matcher_variants_are_bit_identical(hs, oracle, monkeypatch):
     sc, ranges, pts, cnt, truth = make_streams(hs, n, n_scans, seed0=77)
     procs = cpu_streams(oracle, n, dist=0.0, ang=0.0, free=0.4, occ=0.9)
     ref = np.stack([np.stack([p.update(pts[k, s], cnt[k, s], hint=p.pose()) for s, p in enumerate(procs)]) for k in range(n_scans)])
-    for variant in ("1", "2"):
+    for variant in ("1", "2", "3"):
         monkeypatch.setenv("HSGPU_MATCH_VARIANT", variant)
         with hs.Engine(n_streams=n, max_points=360) as eng:
             configure(eng, dist=0.0, ang=0.0, free=0.4, occ=0.9)

@@ -23,5 +23,8 @@ eng.match_batch(pts[K - 1], cnt[K - 1])     # the matcher is the last kernel tha
 eng.close()
 t = np.fromfile(out, dtype=np.uint64).reshape(-1, 8)[:S, :5].astype(np.float64) / 1.965e3   # us at 1965 MHz
 names = ["step1(addr/miss)", "step2(prob)", "step3/points", "sums", "solve+barrier"]
-print("matcher %s: mean per-CTA us over the scan (14 evaluations): " % ("v1" if os.environ.get("HSGPU_MATCH_VARIANT") == "1" else "v2")
-      + "  ".join("%s %.1f" % (n, t[:, i].mean()) for i, n in enumerate(names)) + "  total %.1f" % t.sum(1).mean())
+# thread 0 sits in the serial warp of the CTAs with blockIdx % 4 == 0 (there "sums" and "solve" are the serial work itself); in
+# the other CTAs it is a worker, skips the sums and waits for the serial warp in "solve+barrier"
+for label, sel in (("thread 0 in the serial warp", np.arange(S) % 4 == 0), ("thread 0 in a worker warp", np.arange(S) % 4 != 0)):
+    print("matcher variant %s, %s: mean per-CTA us over the scan (14 evaluations): " % (os.environ.get("HSGPU_MATCH_VARIANT", "default"), label)
+          + "  ".join("%s %.1f" % (n, t[sel, i].mean()) for i, n in enumerate(names)) + "  total %.1f" % t[sel].sum(1).mean())

@@ -200,6 +200,7 @@ int hs_create(const hs_config* cfg, hs_engine** out) {
     int n_sm = 148;
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, cfg->device);
     e->sm_count = n_sm;
+    P.n_sm = n_sm;
     P.tail_slots = 2 * n_sm;   // measured on B200 (148 SMs): 0 -> 179 us, 148 -> 178, 296 -> 176, 444 -> 178.5, 600 -> 181
   }
   if (const char* ts = getenv("HSGPU_RAYCAST_TAIL_SLOTS")) P.tail_slots = atoi(ts) < 0 ? 0 : atoi(ts);
@@ -309,18 +310,19 @@ int hs_create(const hs_config* cfg, hs_engine** out) {
   {
     int smem = hs_match2_pitch(cfg->max_points) * HS_NPROD * (int)sizeof(float);  // k_match's per-CTA product buffer
     if (smem > 48 * 1024) {
-      cudaError_t e1 = cudaFuncSetAttribute(k_match<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-      cudaError_t e2 = cudaFuncSetAttribute(k_match<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      cudaError_t e1 = cudaFuncSetAttribute(k_match<true, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      cudaError_t e2 = cudaFuncSetAttribute(k_match<false, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
       if (e1 != cudaSuccess || e2 != cudaSuccess) {
         hs_destroy(e);
         return (int)(e1 != cudaSuccess ? e1 : e2);
       }
     }
-    // measured on B200: 360 points: k_match 92 us vs k_match2 127 us per 1024 scans; 1440 points: 400 vs 353
-    e->match_variant = cfg->max_points > 768 ? 2 : 1;
+    // measured on B200, per 1024 scans: 360 points: k_match 101 us, k_match with warp-compacted misses (3) 95 us, k_match2 127 us;
+    // 1440 points: k_match 400 us vs k_match2 353 us
+    e->match_variant = cfg->max_points > 768 ? 2 : 3;
     if (const char* mv = getenv("HSGPU_MATCH_VARIANT")) {
       const int v = atoi(mv);
-      if (v == 1 || v == 2) e->match_variant = v;
+      if (v >= 1 && v <= 3) e->match_variant = v;
     }
     int smem2 = (int)match2_smem_for(cfg->max_points);
     if (smem2 > 48 * 1024) {
@@ -521,12 +523,18 @@ static int run_update_device(hs_engine* e, int n, const int32_t* ids, const floa
       else
         k_match2<false><<<n, threads, smem2, st>>>(Pc, n, ids, (const float2*)points, counts, (const float2*)origos, hints, flags, mode);
     } else {
-    const size_t smem = (size_t)hs_match2_pitch(e->P.max_points) * HS_NPROD * sizeof(float);
     int ppt = (e->P.max_points + threads - 1) / threads;   // register-resident points (+ cell caches) per thread
     ppt = ppt <= 2 ? 2 : (ppt <= 3 ? 3 : (ppt <= 6 ? 6 : 0));
+    const bool wc = e->match_variant == 3 && ppt > 0;   // cache misses of a warp processed densely (hs_points_phase_wc)
+    const size_t smem = (size_t)hs_match2_pitch(e->P.max_points) * HS_NPROD * sizeof(float) +
+                        (wc ? (size_t)(threads / 32) * ppt * 160 * sizeof(float) + 32 * sizeof(uint64_t) : 0);
 #define HS_LAUNCH_MATCH(STRICT_, PPT_)                                                               \
-  k_match<STRICT_, PPT_><<<n, threads, smem, st>>>(Pc, n, ids, (const float2*)points, counts, \
-                                                        (const float2*)origos, hints, flags, mode)
+  do {                                                                                               \
+    if (wc) k_match<STRICT_, PPT_, (PPT_ > 0 ? 1 : 0)><<<n, threads, smem, st>>>(Pc, n, ids, (const float2*)points, counts, \
+                                                        (const float2*)origos, hints, flags, mode); \
+    else k_match<STRICT_, PPT_, 0><<<n, threads, smem, st>>>(Pc, n, ids, (const float2*)points, counts, \
+                                                        (const float2*)origos, hints, flags, mode); \
+  } while (0)
 #define HS_LAUNCH_MATCH_S(STRICT_)                                    \
   do {                                                                \
     if (ppt == 2) HS_LAUNCH_MATCH(STRICT_, 2);                        \

@@ -56,6 +56,7 @@ struct HsParams {
   float* hyp_cov;
   int hyp_stream;
   float* host_pose_out;             // non-NULL: the caller's pinned poses_out [slot][3]; the matcher's tail writes the pose there too
+  int n_sm;                         // SM count of the device
   int tail_slots;                   // k_raycast: the last `tail_slots` slots of a launch are dispatched level-major
   int slot0;                        // first slot of this launch (a host batch may be cut into chunks that run on several CUDA streams)
   int dbg_skip;                     // timing experiments only (HSGPU_DEBUG_SKIP): bit0 skip walk, bit1 skip sweep, bit2 skip end points
@@ -337,13 +338,114 @@ __device__ __forceinline__ void hs_store_products(float* __restrict__ q, int pit
   q[8 * pitch] = gy * rot;    // H(1,2)
 }
 
+// Points phase of one evaluation with the cache misses of a WARP processed densely. With the register cache only a few
+// lanes of a warp miss in most evaluations (measured: 3.5 of 32 per point slot), yet every miss drags the whole warp through
+// four inlined probability computations. Here the lanes first publish the block addresses of their misses to a per-warp list
+// in shared memory; the list x 4 corners is then dealt out to all 32 lanes (one gather, one expf, one division per item, four
+// consecutive lanes = the four corners of one block), and the owners read their four probabilities back as one float4.
+// Same values, same order of the per-point arithmetic; only who computes a probability changes.
+//   w_addr: this warp's PPT*32 ints, w_prob: this warp's PPT*128 floats (16-byte aligned), s_tab: expf table in shared memory
+template <int PPT>
+__device__ __forceinline__ void hs_points_phase_wc(const float* __restrict__ val, const HsLevel& L, float ex, float ey, float sn, float cs,
+                                                   const float2* preg, HsCellCache* cache, int n, float pt_factor,
+                                                   float* __restrict__ prod, int pitch, int* __restrict__ w_addr,
+                                                   float* __restrict__ w_prob, const uint64_t* __restrict__ s_tab, int i0, int istride) {
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  unsigned bal[PPT];
+  unsigned mine = 0;   // bit j: slot j missed
+  int total = 0;
+#pragma unroll
+  for (int j = 0; j < PPT; ++j) {
+    const int i = i0 + j * istride;
+    const float px = preg[j].x * pt_factor, py = preg[j].y * pt_factor;
+    const float qx = (cs * px + (-sn) * py) + ex;  // Affine2f * v = linear*v + translation
+    const float qy = (sn * px + cs * py) + ey;
+    bool m = false;
+    if (i < n && qx >= 0.0f && qx <= L.limx && qy >= 0.0f && qy <= L.limy) {  // !pointOutOfMapBounds
+      const int k = (int)qy * L.sx + (int)qx;
+      if (k != cache[j].key) { cache[j].key = k; m = true; }
+    }
+    bal[j] = __ballot_sync(0xffffffffu, m);
+    if (m) {
+      mine |= 1u << j;
+      w_addr[total + __popc(bal[j] & lt)] = cache[j].key;
+    }
+    total += __popc(bal[j]);
+  }
+  if (total) {   // warp-uniform
+    __syncwarp();
+    const int items = total << 2;
+    for (int base = 0; base < items; base += 128) {
+      float v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int q = base + u * 32 + lane;
+        v[u] = 0.0f;
+        if (q < items) {
+          const int k = w_addr[q >> 2];
+          v[u] = __ldg(val + k + (q & 1) + ((q & 2) ? L.sx : 0));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (base + u * 32 < items) {   // warp-uniform
+          const int q = base + u * 32 + lane;
+          const float odds = hs_expf_tab(v[u], s_tab);
+          const float pr = odds / (odds + 1.0f);
+          if (q < items) w_prob[q] = pr;
+        }
+      }
+    }
+    __syncwarp();
+    int off = 0;
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+      if (mine & (1u << j)) {
+        const float4 p4 = reinterpret_cast<const float4*>(w_prob)[off + __popc(bal[j] & lt)];
+        cache[j].p0 = p4.x; cache[j].p1 = p4.y; cache[j].p2 = p4.z; cache[j].p3 = p4.w;
+      }
+      off += __popc(bal[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < PPT; ++j) {
+    const int i = i0 + j * istride;
+    if (i < n) {
+      const float px = preg[j].x * pt_factor, py = preg[j].y * pt_factor;
+      const float qx = (cs * px + (-sn) * py) + ex;
+      const float qy = (sn * px + cs * py) + ey;
+      float m = 0.0f, gx = 0.0f, gy = 0.0f;
+      if (qx >= 0.0f && qx <= L.limx && qy >= 0.0f && qy <= L.limy) {
+        const int ix = (int)qx, iy = (int)qy;
+        const float fx = qx - (float)ix, fy = qy - (float)iy;
+        const float i0 = cache[j].p0, i1 = cache[j].p1, i2 = cache[j].p2, i3 = cache[j].p3;
+        const float dx1 = i0 - i1, dx2 = i2 - i3;
+        const float dy1 = i0 - i2, dy2 = i1 - i3;
+        const float x_inv = 1.0f - fx, y_inv = 1.0f - fy;
+        m = ((i0 * x_inv + i1 * fx) * y_inv) + ((i2 * x_inv + i3 * fx) * fy);
+        gx = -((dx1 * x_inv) + (dx2 * fx));  // the reference blends with the x factors here (OccGridMapUtil.h:344)
+        gy = -((dy1 * y_inv) + (dy2 * fy));  // ... and with the y factors here (:345)
+      }
+      const float fv = 1.0f - m;
+      const float rot = ((-sn * px - cs * py) * gx + (cs * px - sn * py) * gy);
+      hs_store_products(prod + i, pitch, gx, gy, rot, fv);
+    }
+  }
+}
+
 // PPT > 0: the thread's points (i = tid + j*blockDim, j < PPT) are held in registers by the caller (they are the
 // same for all evaluations of a scan); PPT == 0: read them from `pts` (any n).
-template <bool STRICT, int PPT>
+template <bool STRICT, int PPT, int WC = 0>
 __device__ __forceinline__ HsAcc hs_eval_cta(const float* __restrict__ val, const HsLevel& L, float ex, float ey, float sn, float cs,
                                              const float2* __restrict__ pts, const float2* preg, HsCellCache* cache, int n,
-                                             float pt_factor, float* __restrict__ prod, int pitch, int serial_warp = 0, HsMatchTimer* mt = nullptr) {
-  if (PPT > 0) {
+                                             float pt_factor, float* __restrict__ prod, int pitch, int serial_warp = 0, HsMatchTimer* mt = nullptr,
+                                             int* w_addr = nullptr, float* w_prob = nullptr, const uint64_t* s_tab = nullptr,
+                                             int i0 = 0, int istride = 0) {
+  if (PPT > 0 && WC) {
+    if ((i0 & ~31) < n)   // warp-uniform (the phase uses full-warp ballots): skip warps whose first point is past the scan
+      hs_points_phase_wc<(PPT > 0 ? PPT : 1)>(val, L, ex, ey, sn, cs, preg, cache, n, pt_factor, prod, pitch, w_addr, w_prob, s_tab, i0, istride);
+  } else if (PPT > 0) {
 #pragma unroll
     for (int j = 0; j < (PPT > 0 ? PPT : 1); ++j) {
       const int i = threadIdx.x + j * blockDim.x;
@@ -478,7 +580,7 @@ __device__ __forceinline__ void hs_match_tail(const HsParams& P, int slot, int s
 
 // 7 CTAs per SM (<= 72 registers) keeps all 1024 streams of BASELINE configs[1] resident in ONE wave on 148 SMs; at 73+
 // registers the launch needs a second wave and takes 1.5x as long (measured: 94 -> 140 us).
-template <bool STRICT, int PPT>
+template <bool STRICT, int PPT, int WC>
 __global__ void __launch_bounds__(HS_MATCH_THREADS, (PPT > 0 && PPT <= 3) ? 7 : 1) k_match(HsParams P, int n_slots, const int32_t* __restrict__ stream_ids,
                                                             const float2* __restrict__ points, const int32_t* __restrict__ counts,
                                                             const float2* __restrict__ origos, const float* __restrict__ hints,
@@ -488,14 +590,26 @@ __global__ void __launch_bounds__(HS_MATCH_THREADS, (PPT > 0 && PPT <= 3) ? 7 : 
   const int slot = P.slot0 + blockIdx.x;
   const int tid = threadIdx.x;
   if ((int)blockIdx.x >= n_slots) return;
-  // the serial part (sums, 3x3 solve, sin/cos) is carried by ONE warp; which one rotates with the CTA index, so that the
-  // serial warps of the CTAs sharing an SM sit on different SM sub-partitions (warp w issues from scheduler w mod 4)
+  // WC: behind the products, per warp PPT*128 floats (probabilities) and PPT*32 ints (block addresses), then the expf table
+  const int wc_ppt = PPT > 0 ? PPT : 1;
+  float* w_prob = hs_prod + HS_NPROD * hs_match2_pitch(P.max_points) + (tid >> 5) * (wc_ppt * 128);
+  int* w_addr = reinterpret_cast<int*>(hs_prod + HS_NPROD * hs_match2_pitch(P.max_points) + (HS_MATCH_THREADS / 32) * (wc_ppt * 128)) + (tid >> 5) * (wc_ppt * 32);
+  uint64_t* s_tab = reinterpret_cast<uint64_t*>(hs_prod + HS_NPROD * hs_match2_pitch(P.max_points) + (HS_MATCH_THREADS / 32) * (wc_ppt * 160));
+  if (WC && tid < 32) s_tab[tid] = hs_exp2f_tab_dev[tid];   // visible after the first __syncthreads below
+  // the serial part (sums, 3x3 solve, sin/cos) is carried by ONE warp, chosen by the CTA index. CTAs are dealt out to the
+  // SMs breadth first and 148 = 0 mod 4, so the CTAs sharing an SM pick the SAME warp number and their serial warps share
+  // one SM sub-partition (warp w issues from scheduler w mod 4), where their 4-cycle FADD chains interleave. Measured on
+  // B200: spreading them over the four sub-partitions ((blockIdx + blockIdx / n_sm) & 3) costs 5-8 us per launch.
   const int sw = blockIdx.x & ((blockDim.x >> 5) - 1);
   const bool serial = (tid >> 5) == sw, leader = tid == (sw << 5);
   const bool hyp = P.hyp_pose != nullptr;
   const int s = hyp ? P.hyp_stream : hs_slot_stream(stream_ids, slot);
   int n = counts[hyp ? 0 : slot];
   n = n < 0 ? 0 : (n > P.max_points ? P.max_points : n);
+  // point i = i0 + j * istride of the scan is this thread's j-th. (Measured on B200: leaving the serial warp without points,
+  // so that its SM sub-partition only carries the latency-critical chains, and giving the other three warps 4 points per
+  // thread, costs 18 us per launch -- the points phase needs all four sub-partitions.)
+  const int i0 = tid, istride = (int)blockDim.x;
   const float2* pts = points + (hyp ? (size_t)0 : (size_t)slot * P.max_points);
   if (P.stage_pts) {   // zero-copy input: fetch this scan from the caller's pinned host buffer once
     if (P.stage_cnt && tid == 0) P.stage_cnt[slot] = n;
@@ -533,7 +647,7 @@ __global__ void __launch_bounds__(HS_MATCH_THREADS, (PPT > 0 && PPT <= 3) ? 7 : 
       if (PPT > 0) {
 #pragma unroll
         for (int j = 0; j < (PPT > 0 ? PPT : 1); ++j) {
-          const int i = tid + j * blockDim.x;
+          const int i = i0 + j * istride;
           preg[j] = i < n ? pts[i] : make_float2(0.f, 0.f);
         }
       }
@@ -550,7 +664,8 @@ __global__ void __launch_bounds__(HS_MATCH_THREADS, (PPT > 0 && PPT <= 3) ? 7 : 
         __syncthreads();
         for (int it = 0; it <= L.max_iter; ++it) {  // 1 + maxIterations evaluations, no early exit
           const float cex = s_est[0], cey = s_est[1], csn = s_est[3], ccs = s_est[4];
-          a = hs_eval_cta<STRICT, PPT>(val, L, cex, cey, csn, ccs, pts, preg, cache, n, L.pt_factor, hs_prod, hs_match2_pitch(P.max_points), sw, &mt);
+          a = hs_eval_cta<STRICT, PPT, WC>(val, L, cex, cey, csn, ccs, pts, preg, cache, n, L.pt_factor, hs_prod, hs_match2_pitch(P.max_points), sw, &mt,
+                                           w_addr, w_prob, s_tab, i0, istride);
           if (serial) {
             clamps += hs_gauss_newton_step(a, ex, ey, eth) ? 1u : 0u;
             if (leader) { s_est[0] = ex; s_est[1] = ey; s_est[2] = eth; s_est[3] = hs_sinf(eth); s_est[4] = hs_cosf(eth); }
@@ -734,8 +849,10 @@ __global__ void __launch_bounds__(HS_MATCH_THREADS) k_match2(HsParams P, int n_s
   const int slot = P.slot0 + blockIdx.x;
   const int tid = threadIdx.x;
   if ((int)blockIdx.x >= n_slots) return;
-  // the serial part (sums, 3x3 solve, sin/cos) is carried by ONE warp; which one rotates with the CTA index, so that the
-  // serial warps of the CTAs sharing an SM sit on different SM sub-partitions (warp w issues from scheduler w mod 4)
+  // the serial part (sums, 3x3 solve, sin/cos) is carried by ONE warp, chosen by the CTA index. CTAs are dealt out to the
+  // SMs breadth first and 148 = 0 mod 4, so the CTAs sharing an SM pick the SAME warp number and their serial warps share
+  // one SM sub-partition (warp w issues from scheduler w mod 4), where their 4-cycle FADD chains interleave. Measured on
+  // B200: spreading them over the four sub-partitions ((blockIdx + blockIdx / n_sm) & 3) costs 5-8 us per launch.
   const int sw = blockIdx.x & ((blockDim.x >> 5) - 1);
   const bool serial = (tid >> 5) == sw, leader = tid == (sw << 5);
   const bool hyp = P.hyp_pose != nullptr;

@@ -183,8 +183,9 @@ static const uint64_t hs_exp2f_tab_host[32] = HS_EXP2F_TAB_INIT;
 #define HS_EXPF_C1 0x1.ebfce50fac4f3p-13
 #define HS_EXPF_C2 0x1.62e42ff0c52d6p-6
 
-/* e_expf.c */
-HS_HD float hs_expf(float x) {
+/* e_expf.c; `tab` = the 32-entry __exp2f_data.tab (callers on the device may keep a copy in shared memory: lanes of a
+ * warp look up different entries, which a __constant__ bank serialises) */
+HS_HD float hs_expf_tab(float x, const uint64_t* tab) {
   uint32_t abstop = (hs_asuint(x) >> 20) & 0x7ff;
   if (abstop >= ((hs_asuint(88.0f) >> 20) & 0x7ff)) {
     if (hs_asuint(x) == hs_asuint(-INFINITY)) return 0.0f;
@@ -199,11 +200,7 @@ HS_HD float hs_expf(float x) {
   kd = hs_dadd(kd, -HS_EXPF_SHIFT);
   double r = hs_fma(HS_EXPF_INVLN2N, xd, -kd);
   double z;
-#if defined(__CUDA_ARCH__)
-  uint64_t t = hs_exp2f_tab_dev[ki % 32];
-#else
-  uint64_t t = hs_exp2f_tab_host[ki % 32];
-#endif
+  uint64_t t = tab[ki % 32];
   t += ki << (52 - 5);
   double s = hs_asdouble(t);
   z = hs_fma(HS_EXPF_C0, r, HS_EXPF_C1);
@@ -212,6 +209,14 @@ HS_HD float hs_expf(float x) {
   y = hs_fma(z, r2, y);
   y = hs_dmul(y, s);
   return (float)y;
+}
+
+HS_HD float hs_expf(float x) {
+#if defined(__CUDA_ARCH__)
+  return hs_expf_tab(x, hs_exp2f_tab_dev);
+#else
+  return hs_expf_tab(x, hs_exp2f_tab_host);
+#endif
 }
 
 #endif /* HS_LIBM_EXACT_H */
