@@ -154,23 +154,24 @@ def main():
         if not pyoracle.have("port") and not pyoracle.have("ref"):
             pyoracle.build(ref=False)
         sample_streams = max(cores, min(S, 16 * cores))   # a bounded sample of the S streams, every host thread busy
-        steps = W + K
+        # one step = `spp` consecutive scans of each sampled stream: with few steps the timed region would otherwise be a few
+        # milliseconds of thread start-up and first-touch page faults, which understates the CPU
+        spp = max(1, min(64, 1024 // max(W + K, 1)))
+        steps = (W + K) * spp
         _, pts, cnt = gen_inputs(hs, sample_streams, steps, 0xC0FFEE)
-        # warm-up steps are part of the same stream history; time only the K timed steps' worth of work by
-        # timing the whole run and scaling is avoided: run W steps untimed first.
-        kind, _ = ("ref" if pyoracle.have("ref") else "port"), None
+        kind = "ref" if pyoracle.have("ref") else "port"
         procs = [pyoracle.CpuProcessor(kind, 0.05, 1024, 1024, (0.5, 0.5), 3) for _ in range(sample_streams)]
         for p in procs:
             p.set_update_factor_free(NODE_FACTORS[0]); p.set_update_factor_occupied(NODE_FACTORS[1])
             p.set_map_update_min_dist_diff(0.0); p.set_map_update_min_angle_diff(0.0)
-        if W:
-            pyoracle.run_streams(procs, pts[:W], cnt[:W], threads=cores, stream_major=True, want_poses=False)
-        # stream-major order (a thread runs all K scans of one stream before the next stream): the CPU's best case, its
+        if W:   # warm-up steps are part of the same stream histories, run untimed first
+            pyoracle.run_streams(procs, pts[:W * spp], cnt[:W * spp], threads=cores, stream_major=True, want_poses=False)
+        # stream-major order (a thread runs all timed scans of one stream before the next stream): the CPU's best case, its
         # 21 MiB of grids + caches per stream stay in cache
-        secs, _, _ = pyoracle.run_streams(procs, pts[W:], cnt[W:], threads=cores, stream_major=True, want_poses=False)
-        value = sample_streams * K / secs
-        sample = "%d of the %d streams x %d scans, one processor per stream, stream-major order, %d host threads (%s)" % (
-            sample_streams, S, K, cores, "unmodified reference headers, oracle/_ref" if kind == "ref" else "C restatement, oracle/hs_oracle.c")
+        secs, _, _ = pyoracle.run_streams(procs, pts[W * spp:], cnt[W * spp:], threads=cores, stream_major=True, want_poses=False)
+        value = sample_streams * K * spp / secs
+        sample = "%d of the %d streams x %d scans per step, one processor per stream, stream-major order, %d host threads (%s)" % (
+            sample_streams, S, spp, cores, "unmodified reference headers, oracle/_ref" if kind == "ref" else "C restatement, oracle/hs_oracle.c")
         print(json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
                           "ms_per_step": 1e3 * secs / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                           "dtype": "f32", "data": "synthetic", "config": config,

@@ -375,25 +375,23 @@ __device__ __forceinline__ void hs_points_phase_wc(const float* __restrict__ val
   }
   if (total) {   // warp-uniform
     __syncwarp();
-    const int items = total << 2;
-    for (int base = 0; base < items; base += 128) {
+    // item = (miss, corner): lane l always handles corner l & 3 of miss (l >> 2) + 8 * round
+    const int coff = (lane & 1) + ((lane & 2) ? L.sx : 0);
+    const int m0 = lane >> 2;
+    for (int mb = 0; mb < total; mb += 32) {   // 32 misses = 128 items per turn, four gathers in flight per lane
       float v[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int q = base + u * 32 + lane;
+        const int mi = mb + u * 8 + m0;
         v[u] = 0.0f;
-        if (q < items) {
-          const int k = w_addr[q >> 2];
-          v[u] = __ldg(val + k + (q & 1) + ((q & 2) ? L.sx : 0));
-        }
+        if (mi < total) v[u] = __ldg(val + w_addr[mi] + coff);
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        if (base + u * 32 < items) {   // warp-uniform
-          const int q = base + u * 32 + lane;
+        if (mb + u * 8 < total) {   // warp-uniform
           const float odds = hs_expf_tab(v[u], s_tab);
           const float pr = odds / (odds + 1.0f);
-          if (q < items) w_prob[q] = pr;
+          if (mb + u * 8 + m0 < total) w_prob[((mb + u * 8) << 2) + lane] = pr;
         }
       }
     }
