@@ -379,6 +379,10 @@ def test_point_cloud_entry_point_equals_oracle_pipeline(hs, oracle):
             ref = p.update(cp, len(cp), origo=co, hint=p.pose())
             assert np.array_equal(bits(out[s]), bits(ref)), (k, s)
     assert_same_maps(eng, procs, 3)
+    # 1..3 points: a singular Hessian, where the reference itself indexes its grid with (int)NaN -- no oracle, just no hang
+    tiny = np.array([1 + (s % 3) for s in range(n)], np.int32)
+    eng.update_batch(np.ascontiguousarray(long_pts[0]), tiny)
+    eng.synchronize()
     eng.close()
     for p in procs:
         p.close()
@@ -554,3 +558,35 @@ def test_pinned_ranges_entry_point_deferred_and_synchronous_identical(hs, monkey
         assert np.array_equal(bits(r[0]), bits(results[-1][0])) and np.array_equal(bits(r[1]), bits(results[-1][1]))
         for (a, ai), (b, bi) in zip(r[2], results[-1][2]):
             assert np.array_equal(bits(a), bits(b)) and np.array_equal(ai, bi)
+
+
+@pytest.mark.parametrize("max_points", [40, 200, 360, 700, 900])
+def test_every_matcher_instantiation_with_ragged_counts(hs, oracle, max_points):
+    """The matcher is compiled once per points-per-thread class (max_points <= 256: 2, <= 384: 3, <= 768: 6; above: k_match2)
+    and its cache-miss pass uses full-warp ballots: scans whose length ends inside a warp, inside the first warp, exactly on a
+    warp or CTA boundary, or at 0 / 1 / max_points points must neither hang nor differ from the oracle."""
+    n, n_scans = 12, 5
+    sc, ranges, pts, cnt, truth = make_streams(hs, n, 2 * n_scans, seed0=6100 + max_points)
+    # scans longer than 360 points: two consecutive scans of a stream back to back (same room, nearly the same pose)
+    long_pts = np.concatenate([pts[0::2], pts[1::2]], axis=2)[:, :, :max_points].copy()      # [n_scans][n][<=720][2]
+    if long_pts.shape[2] < max_points:
+        long_pts = np.concatenate([long_pts, long_pts[:, :, :max_points - long_pts.shape[2]]], axis=2)
+    lengths = [0, 30, 31, 32, 33, 64, 127, 128, 129, max_points - 1, max_points, max_points // 2]
+    counts = np.array([[min(lengths[(s + k) % len(lengths)], max_points) for s in range(n)] for k in range(n_scans)], np.int32)
+    counts[0] = max_points     # a full first scan, so that there is a map to match the ragged ones against
+    eng, procs = setup_pair(hs, oracle, n, max_points=max_points)
+    for k in range(n_scans):
+        out, cov = eng.update_batch(np.ascontiguousarray(long_pts[k]), counts[k])
+        for s, p in enumerate(procs):
+            ref = p.update(long_pts[k, s], counts[k, s], hint=p.pose())
+            assert np.array_equal(bits(out[s]), bits(ref)), (k, s, counts[k, s])
+            if counts[k, s]:
+                assert np.array_equal(bits(cov[s]), bits(p.cov())), (k, s, counts[k, s])
+    assert_same_maps(eng, procs, 3)
+    # 1..3 points: a singular Hessian, where the reference itself indexes its grid with (int)NaN -- no oracle, just no hang
+    tiny = np.array([1 + (s % 3) for s in range(n)], np.int32)
+    eng.update_batch(np.ascontiguousarray(long_pts[0]), tiny)
+    eng.synchronize()
+    eng.close()
+    for p in procs:
+        p.close()
