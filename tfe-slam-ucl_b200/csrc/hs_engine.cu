@@ -201,6 +201,8 @@ int hs_create(const hs_config* cfg, hs_engine** out) {
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, cfg->device);
     e->sm_count = n_sm;
     P.n_sm = n_sm;
+    P.l2_keep_levels = 0xFF;
+    if (const char* k = getenv("HSGPU_MATCH_L2_LEVELS")) P.l2_keep_levels = atoi(k);
     P.tail_slots = 2 * n_sm;   // measured on B200 (148 SMs): 0 -> 179 us, 148 -> 178, 296 -> 176, 444 -> 178.5, 600 -> 181
   }
   if (const char* ts = getenv("HSGPU_RAYCAST_TAIL_SLOTS")) P.tail_slots = atoi(ts) < 0 ? 0 : atoi(ts);

@@ -57,6 +57,7 @@ struct HsParams {
   int hyp_stream;
   float* host_pose_out;             // non-NULL: the caller's pinned poses_out [slot][3]; the matcher's tail writes the pose there too
   int n_sm;                         // SM count of the device
+  int l2_keep_levels;               // bit l: the matcher's gathers on level l carry an L2 evict-last hint
   int tail_slots;                   // k_raycast: the last `tail_slots` slots of a launch are dispatched level-major
   int slot0;                        // first slot of this launch (a host batch may be cut into chunks that run on several CUDA streams)
   int dbg_skip;                     // timing experiments only (HSGPU_DEBUG_SKIP): bit0 skip walk, bit1 skip sweep, bit2 skip end points
@@ -338,6 +339,20 @@ __device__ __forceinline__ void hs_store_products(float* __restrict__ q, int pit
   q[8 * pitch] = gy * rot;    // H(1,2)
 }
 
+// Gather of a log-odds value with an L2 evict-last hint: the cells around the scan end points are read again by the next
+// scan's match (the robot moves a few cells per scan), while the ray-caster streams half a gigabyte of other lines through
+// L2 in between.
+__device__ __forceinline__ float hs_ldg_evict_last(const float* p, unsigned long long policy) {
+  float v;
+  asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(policy));
+  return v;
+}
+__device__ __forceinline__ unsigned long long hs_policy_evict_last() {
+  unsigned long long policy;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
+  return policy;
+}
+
 // Points phase of one evaluation with the cache misses of a WARP processed densely. With the register cache only a few
 // lanes of a warp miss in most evaluations (measured: 3.5 of 32 per point slot), yet every miss drags the whole warp through
 // four inlined probability computations. Here the lanes first publish the block addresses of their misses to a per-warp list
@@ -349,7 +364,8 @@ template <int PPT>
 __device__ __forceinline__ void hs_points_phase_wc(const float* __restrict__ val, const HsLevel& L, float ex, float ey, float sn, float cs,
                                                    const float2* preg, HsCellCache* cache, int n, float pt_factor,
                                                    float* __restrict__ prod, int pitch, int* __restrict__ w_addr,
-                                                   float* __restrict__ w_prob, const uint64_t* __restrict__ s_tab, int i0, int istride) {
+                                                   float* __restrict__ w_prob, const uint64_t* __restrict__ s_tab, int i0, int istride,
+                                                   bool keep_in_l2) {
   const int lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
   unsigned bal[PPT];
@@ -378,13 +394,14 @@ __device__ __forceinline__ void hs_points_phase_wc(const float* __restrict__ val
     // item = (miss, corner): lane l always handles corner l & 3 of miss (l >> 2) + 8 * round
     const int coff = (lane & 1) + ((lane & 2) ? L.sx : 0);
     const int m0 = lane >> 2;
+    const unsigned long long pol = hs_policy_evict_last();
     for (int mb = 0; mb < total; mb += 32) {   // 32 misses = 128 items per turn, four gathers in flight per lane
       float v[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int mi = mb + u * 8 + m0;
         v[u] = 0.0f;
-        if (mi < total) v[u] = __ldg(val + w_addr[mi] + coff);
+        if (mi < total) v[u] = keep_in_l2 ? hs_ldg_evict_last(val + w_addr[mi] + coff, pol) : __ldg(val + w_addr[mi] + coff);
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -439,10 +456,10 @@ __device__ __forceinline__ HsAcc hs_eval_cta(const float* __restrict__ val, cons
                                              const float2* __restrict__ pts, const float2* preg, HsCellCache* cache, int n,
                                              float pt_factor, float* __restrict__ prod, int pitch, int serial_warp = 0, HsMatchTimer* mt = nullptr,
                                              int* w_addr = nullptr, float* w_prob = nullptr, const uint64_t* s_tab = nullptr,
-                                             int i0 = 0, int istride = 0) {
+                                             int i0 = 0, int istride = 0, bool keep_in_l2 = false) {
   if (PPT > 0 && WC) {
     if ((i0 & ~31) < n)   // warp-uniform (the phase uses full-warp ballots): skip warps whose first point is past the scan
-      hs_points_phase_wc<(PPT > 0 ? PPT : 1)>(val, L, ex, ey, sn, cs, preg, cache, n, pt_factor, prod, pitch, w_addr, w_prob, s_tab, i0, istride);
+      hs_points_phase_wc<(PPT > 0 ? PPT : 1)>(val, L, ex, ey, sn, cs, preg, cache, n, pt_factor, prod, pitch, w_addr, w_prob, s_tab, i0, istride, keep_in_l2);
   } else if (PPT > 0) {
 #pragma unroll
     for (int j = 0; j < (PPT > 0 ? PPT : 1); ++j) {
@@ -663,7 +680,7 @@ __global__ void __launch_bounds__(HS_MATCH_THREADS, (PPT > 0 && PPT <= 3) ? 7 : 
         for (int it = 0; it <= L.max_iter; ++it) {  // 1 + maxIterations evaluations, no early exit
           const float cex = s_est[0], cey = s_est[1], csn = s_est[3], ccs = s_est[4];
           a = hs_eval_cta<STRICT, PPT, WC>(val, L, cex, cey, csn, ccs, pts, preg, cache, n, L.pt_factor, hs_prod, hs_match2_pitch(P.max_points), sw, &mt,
-                                           w_addr, w_prob, s_tab, i0, istride);
+                                           w_addr, w_prob, s_tab, i0, istride, ((P.l2_keep_levels >> level) & 1) != 0);
           if (serial) {
             clamps += hs_gauss_newton_step(a, ex, ey, eth) ? 1u : 0u;
             if (leader) { s_est[0] = ex; s_est[1] = ey; s_est[2] = eth; s_est[3] = hs_sinf(eth); s_est[4] = hs_cosf(eth); }
