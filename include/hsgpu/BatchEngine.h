@@ -64,6 +64,12 @@ class BatchEngine {
     check(hs_submit_batch(e_, n, stream_ids, points, counts, origos, poseHints, map_without_matching, poses_out), "hs_submit_batch");
   }
   void wait() { check(hs_wait(e_), "hs_wait"); }
+  // multi-start matchData of one scan against one stream's maps (relocalisation): n_hyp world pose hints in, as many matched
+  // poses (and level-0 Hessians) out; the stream's state is not touched (hs_match_hypotheses)
+  void matchHypotheses(int stream, const float* points, int n_points, const float* poseHints, int n_hyp, float* poses_out,
+                       float* cov_out = nullptr) {
+    check(hs_match_hypotheses(e_, stream, points, n_points, poseHints, n_hyp, poses_out, cov_out), "hs_match_hypotheses");
+  }
 
   // getLastScanMatchPose / getLastScanMatchCovariance (HectorSlamProcessor.h:126-127) of streams [first, first + n)
   std::vector<float> lastScanMatchPoses(int first, int n) {
