@@ -347,6 +347,11 @@ __device__ __forceinline__ float hs_ldg_evict_last(const float* p, unsigned long
   asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(policy));
   return v;
 }
+__device__ __forceinline__ unsigned long long hs_policy_evict_normal() {
+  unsigned long long policy;
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(policy));
+  return policy;
+}
 __device__ __forceinline__ unsigned long long hs_policy_evict_last() {
   unsigned long long policy;
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
@@ -394,14 +399,14 @@ __device__ __forceinline__ void hs_points_phase_wc(const float* __restrict__ val
     // item = (miss, corner): lane l always handles corner l & 3 of miss (l >> 2) + 8 * round
     const int coff = (lane & 1) + ((lane & 2) ? L.sx : 0);
     const int m0 = lane >> 2;
-    const unsigned long long pol = hs_policy_evict_last();
+    const unsigned long long pol = keep_in_l2 ? hs_policy_evict_last() : hs_policy_evict_normal();
     for (int mb = 0; mb < total; mb += 32) {   // 32 misses = 128 items per turn, four gathers in flight per lane
       float v[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int mi = mb + u * 8 + m0;
         v[u] = 0.0f;
-        if (mi < total) v[u] = keep_in_l2 ? hs_ldg_evict_last(val + w_addr[mi] + coff, pol) : __ldg(val + w_addr[mi] + coff);
+        if (mi < total) v[u] = hs_ldg_evict_last(val + w_addr[mi] + coff, pol);
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
