@@ -367,6 +367,7 @@ def main():
                "dtype": "f32", "data": "synthetic", "config": config, "impl": "ours",
                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step,
                        "api": "hs_update_batch (host pointers, pinned)", "pose_checksum": pose_checksum,
+                       "sync": "every call returns with its poses in host memory; its map integration finishes on the engine's stream, ordered before the next call's match; the timed region ends with a device synchronisation",
                        "ranges_api": {"value": e2e_rng_scans / e2e_rng_max_s, "h2d_bytes_per_step": rng_step, "d2h_bytes_per_step": d2h_step,
                                       "api": "hs_update_batch_ranges (LaserScan ranges in, conversion on the GPU)",
                                       "pose_checksum": ranges_checksum},
