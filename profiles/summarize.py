@@ -49,7 +49,7 @@ def launches(tag, path):
             cur = collections.OrderedDict()
             legs.append(cur)
         cur.setdefault(name, []).append(us)
-    leg_names = ["inputs resident in HBM (bench `value`, `roofline`)", "hs_update_batch, pinned host buffers read zero-copy (bench `e2e`)",
+    leg_names = ["inputs resident in HBM (bench `value`, `roofline`)", "hs_update_batch, pinned host buffers, deferred integration (bench `e2e`)",
                  "hs_update_batch_ranges (bench `e2e.ranges_api`)", "hs_submit_batch / hs_wait, DMA on a copy stream (bench `e2e.pipelined_api`)"]
     with open(os.path.join(HERE, tag + "_launches.md"), "w") as f:
         f.write("# %s: every launch with its device time (ncu --metrics gpu__time_duration.sum --clock-control none)\n\n" % tag)
