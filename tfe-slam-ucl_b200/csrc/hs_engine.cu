@@ -25,6 +25,7 @@ struct hs_engine {
   cudaStream_t stream;
   // host batches are cut into chunks whose host-to-device copies overlap the kernels of the previous chunk
   int e2e_chunks, e2e_first_pct, e2e_zero_copy, e2e_defer, sm_count = 148;
+  int ray_alternate = 1; unsigned ray_launches = 0;   // k_raycast slot order alternates between launches
   int prof_every = 1; unsigned prof_tick = 0;   // kernel events around every prof_every-th update only
   cudaEvent_t ev_match = nullptr;
   cudaStream_t aux_stream[HS_MAX_CHUNKS - 1];
@@ -202,6 +203,8 @@ int hs_create(const hs_config* cfg, hs_engine** out) {
     e->sm_count = n_sm;
     P.n_sm = n_sm;
     P.l2_keep_levels = 0xFF;
+    P.reverse_order = 0;
+    if (const char* ra = getenv("HSGPU_RAYCAST_ALTERNATE")) e->ray_alternate = atoi(ra) != 0;
     // The matcher's evict-last gathers live in the persisting part of L2. Measured on B200 (k_raycast us per launch): 0 MB 170,
     // 8 MB 167, 16 MB 164, 24 MB (this driver's default) 165, 32 MB 173, 64 MB 271 -- a large set-aside starves the
     // ray-caster's streaming traffic. A process that has chosen a size keeps it; only an unset (0) limit is raised.
@@ -563,6 +566,7 @@ static int run_update_device(hs_engine* e, int n, const int32_t* ids, const floa
   HS_LAUNCHED(e);
   if (ev_matched) HS_CK(cudaEventRecord(ev_matched, st));
   if (mode == 0) {
+    Pc.reverse_order = e->ray_alternate ? (int)(e->ray_launches++ & 1u) : 0;
     {
       ProfScope ps(e, HS_K_RAYCAST);
       k_raycast<<<n * e->P.n_levels, HS_RAYCAST_THREADS, raycast_smem(e), st>>>(

@@ -57,6 +57,7 @@ struct HsParams {
   int hyp_stream;
   float* host_pose_out;             // non-NULL: the caller's pinned poses_out [slot][3]; the matcher's tail writes the pose there too
   int n_sm;                         // SM count of the device
+  int reverse_order;                // k_raycast: this launch walks the slots from the last to the first
   int l2_keep_levels;               // bit l: the matcher's gathers on level l carry an L2 evict-last hint
   int tail_slots;                   // k_raycast: the last `tail_slots` slots of a launch are dispatched level-major
   int slot0;                        // first slot of this launch (a host batch may be cut into chunks that run on several CUDA streams)
@@ -1312,8 +1313,11 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS, 3) k_raycast(HsParams P, i
       level = r / n_tail;
       local = n_head + (r - level * n_tail);
     }
-    slot = P.slot0 + local;
     if (local >= n_slots || level >= P.n_levels) return;
+    // consecutive launches walk the slots in opposite directions: the grids of the streams integrated LAST by one launch
+    // are still in L2 when the next launch starts with them
+    if (P.reverse_order) local = n_slots - 1 - local;
+    slot = P.slot0 + local;
   }
   hs_stamp(P, 0);
   // Everything this CTA needs from global memory is requested up front, BEFORE the gate flag is tested: the loads are
