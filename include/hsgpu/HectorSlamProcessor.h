@@ -116,7 +116,7 @@ class GridMap {
   Eigen::Vector3f getMapCoordsPose(const Eigen::Vector3f& w) const { return Eigen::Vector3f(scale_ * w[0] + tmx_, scale_ * w[1] + tmy_, w[2]); }
 
  private:
-  friend class HectorSlamProcessor;
+  friend class HectorSlamProcessor;   // fills the mirror (also for hsgpu/MapRepGpu.h, which derives from it)
   Eigen::Vector2i dims_;
   float cell_length_, scale_, tmx_, tmy_, a_, twx_, twy_;
   int update_index_;
@@ -264,6 +264,8 @@ class HectorSlamProcessor {
   hs_engine* engine() { return engine_; }  // escape hatch to the C ABI (statistics, device variants)
 
  protected:
+  void setLevelUpdateIndex(size_t level, int updateIndex) { levels_[level].update_index_ = updateIndex; }   // for hsgpu/MapRepGpu.h
+
   hs_engine* engine_;
   mutable std::mutex engine_mutex_;
   mutable std::vector<GridMap> levels_;

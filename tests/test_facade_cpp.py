@@ -118,3 +118,60 @@ def test_batch_engine_matches_oracle(tmp_path, hs, oracle):
         ref = procs[s].download_level(0)
         assert ui == procs[s].update_index(0)
         assert np.array_equal(cells["updateIndex"], ref["updateIndex"]) and np.array_equal(bits(cells["logOddsVal"]), bits(ref["logOddsVal"]))
+
+
+def build_maprep_test(tmp_path, hs):
+    exe = str(tmp_path / "maprep_test")
+    libdir = os.path.dirname(hs.LIB_PATH)
+    cmd = ["g++", "-std=c++14", "-O2", "-ffp-contract=off", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "oracle", "shim"),
+           "-o", exe, os.path.join(ROOT, "tests", "cpp", "maprep_test.cpp"), "-L", libdir, "-lhsgpu", "-Wl,-rpath," + libdir, "-pthread"]
+    subprocess.run(cmd, check=True)
+    return exe
+
+
+def test_maprep_gpu_compiles_and_fails_loudly_without_gpu(tmp_path, hs):
+    """include/hsgpu/MapRepGpu.h implements the reference's MapRepresentationInterface (the seam below the processor)."""
+    exe = build_maprep_test(tmp_path, hs)
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by test_maprep_gpu_matches_oracle")
+    inp = tmp_path / "in.bin"
+    inp.write_bytes(np.array([0, 4], np.int32).tobytes())
+    res = subprocess.run([exe, str(inp), str(tmp_path / "out.bin")], capture_output=True, text=True)
+    assert res.returncode != 0 and "no usable CUDA device" in res.stderr
+
+
+@pytest.mark.gpu
+def test_maprep_gpu_matches_oracle(tmp_path, hs, oracle):
+    """matchData + host-side gate + updateByScan through MapRepresentationInterface == the reference's update(), bit for bit
+    (node thresholds 0.4 m / 0.9 rad, so some scans are matched but not integrated)."""
+    exe = build_maprep_test(tmp_path, hs)
+    n_scans, mp = 120, 360
+    sc, ranges, pts, cnt, truth = make_streams(hs, 1, n_scans, seed0=909)
+    with open(tmp_path / "in.bin", "wb") as f:
+        f.write(np.array([n_scans, mp], np.int32).tobytes())
+        for k in range(n_scans):
+            f.write(np.array([cnt[k, 0]], np.int32).tobytes())
+            f.write(pts[k, 0].astype(np.float32).tobytes())
+    res = subprocess.run([exe, str(tmp_path / "in.bin"), str(tmp_path / "out.bin")], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    raw = open(tmp_path / "out.bin", "rb").read()
+    rows = np.frombuffer(raw[: n_scans * 48], np.float32).reshape(n_scans, 12)
+    p = oracle.CpuProcessor("port")
+    p.set_update_factor_free(0.4); p.set_update_factor_occupied(0.9)
+    p.set_map_update_min_dist_diff(0.4); p.set_map_update_min_angle_diff(0.9)
+    for k in range(n_scans):
+        pose = p.update(pts[k, 0], cnt[k, 0], hint=p.pose())
+        assert np.array_equal(bits(rows[k, :3]), bits(pose)), k
+        if k > 0:
+            assert np.array_equal(bits(rows[k, 3:]), bits(p.cov().reshape(-1))), k
+    assert 1 <= p.update_index(0) < n_scans - 1         # the gate both passed (more than the first scan) and held back scans
+    off = n_scans * 48
+    for l in range(3):
+        sx, sy, ui = np.frombuffer(raw[off: off + 12], np.int32)
+        off += 12
+        cells = np.frombuffer(raw[off: off + sx * sy * 8], oracle.CELL_DTYPE)
+        off += sx * sy * 8
+        ref = p.download_level(l)
+        assert (sx, sy) == p.level_dims(l)[:2] and ui == p.update_index(l)
+        assert np.array_equal(cells["updateIndex"], ref["updateIndex"]) and np.array_equal(bits(cells["logOddsVal"]), bits(ref["logOddsVal"]))
