@@ -440,11 +440,11 @@ __device__ __forceinline__ void hs_points_phase_wc(const float* __restrict__ val
       if (qx >= 0.0f && qx <= L.limx && qy >= 0.0f && qy <= L.limy) {
         const int ix = (int)qx, iy = (int)qy;
         const float fx = qx - (float)ix, fy = qy - (float)iy;
-        const float i0 = cache[j].p0, i1 = cache[j].p1, i2 = cache[j].p2, i3 = cache[j].p3;
-        const float dx1 = i0 - i1, dx2 = i2 - i3;
-        const float dy1 = i0 - i2, dy2 = i1 - i3;
+        const float v0 = cache[j].p0, v1 = cache[j].p1, v2 = cache[j].p2, v3 = cache[j].p3;   // intensities[0..3] (:318-335)
+        const float dx1 = v0 - v1, dx2 = v2 - v3;
+        const float dy1 = v0 - v2, dy2 = v1 - v3;
         const float x_inv = 1.0f - fx, y_inv = 1.0f - fy;
-        m = ((i0 * x_inv + i1 * fx) * y_inv) + ((i2 * x_inv + i3 * fx) * fy);
+        m = ((v0 * x_inv + v1 * fx) * y_inv) + ((v2 * x_inv + v3 * fx) * fy);
         gx = -((dx1 * x_inv) + (dx2 * fx));  // the reference blends with the x factors here (OccGridMapUtil.h:344)
         gy = -((dy1 * y_inv) + (dy2 * fy));  // ... and with the y factors here (:345)
       }
