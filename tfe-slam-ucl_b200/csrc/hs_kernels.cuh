@@ -593,10 +593,11 @@ __device__ __forceinline__ void hs_match_tail(const HsParams& P, int slot, int s
 //   MapRepMultiMap::matchData (MapRepMultiMap.h:116-132) -> ScanMatcher::matchData per level, coarse to fine
 //   (ScanMatcher.h:54-190), then the poseDifferenceLargerThan gate and the per-stream bookkeeping.
 // One CTA owns one stream for the whole coarse-to-fine solve (14 evaluations for 3 levels); the pose estimate
-// lives in shared memory and nothing returns to the host in between. Warp 0 carries the serial part
+// lives in shared memory and nothing returns to the host in between. One warp carries the serial part
 // (sums, 3x3 solve, sin/cos of the new angle); the other warps only help with the per-point gathers.
 // mode: 0 = update (match + gate), 1 = match only (no gate, no integration).
-// dynamic shared memory: max_points * 9 floats.
+// dynamic shared memory: 9 * pitch floats (products, sum-major) | WC: per warp PPT*128 floats + PPT*32 ints | WC: 32 x 8 B expf table.
+// WC = 1: the cache misses of a warp are processed densely (hs_points_phase_wc); 0: every thread converts its own misses.
 #define HS_MATCH_THREADS 128   // measured on B200 at 1024 streams: 64 -> 160 us, 96 -> 122, 128 -> 109, 192/256 -> 143 per launch
 
 // 7 CTAs per SM (<= 72 registers) keeps all 1024 streams of BASELINE configs[1] resident in ONE wave on 148 SMs; at 73+
