@@ -37,7 +37,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "scans matched+integrated/sec (360-beam, 3-level 1024^2 grid)"
 UNIT = "scans/s"
-PROF_EVERY = 4   # per-kernel CUDA events around every 4th timed step (event pairs keep consecutive kernels from overlapping)
+PROF_EVERY = 8   # per-kernel CUDA events around every 8th timed step (event pairs keep consecutive kernels from overlapping)
 NODE_FACTORS = (0.4, 0.9)  # HectorMappingRos.cpp:72-73
 E_EVALS = 14               # 4*(L-1)+6 evaluations per scan, L=3
 FALLBACK_HBM_GBS = 6650.0  # B200_PROFILING.md fallback
