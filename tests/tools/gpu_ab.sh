@@ -4,6 +4,7 @@
 set -u
 R=${1:-2}; K=${2:-200}
 LIB=tfe-slam-ucl_b200/libhsgpu.so
+mkdir -p tmp_ab   # tmp_ab/libhsgpu_old.so: build A with `make -C tfe-slam-ucl_b200/csrc OUT=$PWD/tmp_ab/libhsgpu_old.so` before editing
 cp $LIB tmp_ab/libhsgpu_new.so
 run() {
   cp tmp_ab/libhsgpu_$1.so $LIB
