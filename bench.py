@@ -35,6 +35,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+import workload  # noqa: E402  synthetic scan streams (workload/libhsscangen.so): shared by both arms, loads no CUDA library
+
 METRIC = "scans matched+integrated/sec (360-beam, 3-level 1024^2 grid)"
 UNIT = "scans/s"
 PROF_EVERY = 8   # per-kernel CUDA events around every 8th timed step (event pairs keep consecutive kernels from overlapping)
@@ -110,10 +112,10 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def gen_inputs(hs, n_streams, n_steps, seed0):
-    sc = hs.scene_preset(hs.SCENE_RPLIDAR_ROOM)
-    ranges, _ = hs.scangen_batch(sc, seed0, n_streams, 0, n_steps, truth=False)
-    pts, cnt = hs.scan_to_points_host(ranges, sc, 20.0)  # scaleToMap = 1/0.05
+def gen_inputs(n_streams, n_steps, seed0):
+    sc = workload.scene_preset(workload.SCENE_RPLIDAR_ROOM)
+    ranges, _ = workload.scangen_batch(sc, seed0, n_streams, 0, n_steps, truth=False)
+    pts, cnt = workload.scan_to_points_host(ranges, sc, 20.0)  # scaleToMap = 1/0.05
     return sc, pts, cnt
 
 
@@ -149,7 +151,6 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        import tfe_slam_ucl_b200 as hs
         from oracle import pyoracle
         if not pyoracle.have("port") and not pyoracle.have("ref"):
             pyoracle.build(ref=False)
@@ -158,7 +159,7 @@ def main():
         # milliseconds of thread start-up and first-touch page faults, which understates the CPU
         spp = max(1, min(64, 1024 // max(W + K, 1)))
         steps = (W + K) * spp
-        _, pts, cnt = gen_inputs(hs, sample_streams, steps, 0xC0FFEE)
+        _, pts, cnt = gen_inputs(sample_streams, steps, 0xC0FFEE)
         kind = "ref" if pyoracle.have("ref") else "port"
         procs = [pyoracle.CpuProcessor(kind, 0.05, 1024, 1024, (0.5, 0.5), 3) for _ in range(sample_streams)]
         for p in procs:
@@ -208,7 +209,7 @@ def main():
     t_gen = time.time()
     first_stream, n_local = sharding.shard_range(world * S, world, rank)   # this rank's block of the global streams
     assert n_local == S
-    sc, pts, cnt = gen_inputs(hs, S, steps, 0xC0FFEE + first_stream)
+    sc, pts, cnt = gen_inputs(S, steps, 0xC0FFEE + first_stream)
     t_gen = time.time() - t_gen
 
     eng = hs.Engine(0.05, 1024, 1024, (0.5, 0.5), 3, n_streams=S, max_points=360, device=local_rank)
@@ -284,7 +285,7 @@ def main():
     # ---- leg 2b (informational): the same, but the caller hands over LaserScan ranges and the engine does
     # rosLaserScanToDataContainer on the GPU (hs_update_batch_ranges): half the host-to-device bytes
     eng.reset()
-    ranges_all, _ = hs.scangen_batch(sc, 0xC0FFEE + first_stream, S, 0, steps, truth=False)
+    ranges_all, _ = workload.scangen_batch(sc, 0xC0FFEE + first_stream, S, 0, steps, truth=False)
     eng.set_scan_geometry(sc.n_beams, sc.angle_min, sc.angle_increment, sc.range_min, sc.range_max)
     h_rng = torch.from_numpy(ranges_all).pin_memory()
     rng_step = h_rng[0].numel() * 4

@@ -53,7 +53,9 @@ typedef struct {
   float start_y;        /* startCoords.y */
   int32_t levels;       /* multi_res_size, 1..HS_MAX_LEVELS */
   int32_t n_streams;    /* independent processors held by this engine */
-  int32_t max_points;   /* capacity of one DataContainer (beams per scan) */
+  int32_t max_points;   /* capacity of one DataContainer (beams per scan); bounded by the ray-caster's shared memory
+                           (48 KB map + 8 B x hash size + 32 B per point <= the device's opt-in limit: 3679 on B200),
+                           larger values are refused with HS_ERR_INVALID_ARG */
   int32_t device;       /* CUDA device ordinal */
 } hs_config;
 
@@ -92,7 +94,10 @@ const char* hs_status_string(int status);
 
 /* HectorSlamProcessor::update (HectorSlamProcessor.h:71-113) for n streams in one launch sequence:
  * MapRepMultiMap::matchData -> poseDifferenceLargerThan gate -> MapRepMultiMap::updateByScan.
- *   stream_ids           [n] engine stream index of each slot, or NULL for 0..n-1 (ids must be distinct)
+ *   stream_ids           [n] engine stream index of each slot, or NULL for 0..n-1. Ids must be in range and DISTINCT (two
+ *                        slots on one stream would race on its maps): every host-pointer entry point checks this and
+ *                        returns HS_ERR_INVALID_ARG; the *_device variants cannot look at device memory without a
+ *                        synchronisation and leave the requirement to the caller
  *   points               [n][max_points][2] DataContainer points (level-0 cells), only counts[i] used
  *   counts               [n] DataContainer::getSize()
  *   origos               [n][2] DataContainer::getOrigo(), or NULL for (0,0)
@@ -186,6 +191,12 @@ int hs_match_batch(hs_engine* e, int n, const int32_t* stream_ids, const float* 
  * matchData's setFrom would (MapRepMultiMap.h:127). Does not touch lastMapUpdatePose. Host pointers. */
 int hs_raycast_batch(hs_engine* e, int n, const int32_t* stream_ids, const float* points, const int32_t* counts,
                      const float* origos, const float* poses_world);
+/* MapRepMultiMap::updateByScan + onMapUpdated (MapRepMultiMap.h:107-114,134-147) exactly: level 0 integrates `points`,
+ * level i > 0 integrates dataContainers[i-1] AS THE LAST matchData LEFT IT (possibly a different scan, or empty when no
+ * match has run yet) -- what a caller sees that drives the reference's MapRepresentationInterface::updateByScan itself,
+ * e.g. HectorSlamProcessor::update(..., map_without_matching = true). Same arguments as hs_raycast_batch. Host pointers. */
+int hs_integrate_batch(hs_engine* e, int n, const int32_t* stream_ids, const float* points, const int32_t* counts,
+                       const float* origos, const float* poses_world);
 
 /* nav_msgs/OccupancyGrid metadata of a level as HectorMappingRos::setServiceGetMapData fills it
  * (HectorMappingRos.cpp:544-560): origin = getWorldCoords(0,0) - cellLength/2, resolution = getCellLength(), width/height
@@ -270,28 +281,8 @@ int hs_profile_enable(hs_engine* e, int on);
 /* Waits for the stream, sums the elapsed time per kernel since the last collect/enable, and clears the log. */
 int hs_profile_collect(hs_engine* e, hs_kernel_times* out);
 
-/* ---- deterministic synthetic scan streams (host code) ------------- */
-
-typedef struct {
-  int32_t n_beams;
-  float angle_min, angle_increment;
-  float range_min, range_max;
-  float noise_sigma;       /* Gaussian range noise [m] */
-  float room_w, room_h;    /* axis-aligned room centred at the origin [m] */
-  int32_t n_boxes;         /* axis-aligned box obstacles */
-  float box_min, box_max;  /* box edge length range [m] */
-  float traj_rx, traj_ry;  /* ellipse radii of the closed-loop trajectory [m] */
-  int32_t traj_period;     /* scans per loop */
-} hs_scene_config;
-
-#define HS_SCENE_RPLIDAR_ROOM 0 /* 360 beams 0..359 deg, 0.15-12 m, 10 m x 8 m room, 6 boxes (configs 1,2,5) */
-#define HS_SCENE_HIRES_HALL 1   /* 1440 beams, 30 m, 40 m x 30 m hall, 12 boxes (config 3) */
-int hs_scene_preset(int preset, hs_scene_config* out);
-/* ranges [n_scans][n_streams][n_beams] for streams seed0 + s (s in [0, n_streams)) and scans
- * [first_scan, first_scan+n_scans); truth_poses [n_scans][n_streams][3] (relative to each stream's
- * first pose) or NULL. Deterministic in (cfg, seed, scan, beam); `threads` host threads. */
-int hs_scangen_batch(const hs_scene_config* cfg, uint64_t seed0, int n_streams, int first_scan, int n_scans,
-                     float* ranges, float* truth_poses, int threads);
+/* The deterministic synthetic scan streams the tests and bench.py feed the engine are NOT part of this library:
+ * include/hsscangen.h, workload/libhsscangen.so. */
 
 #ifdef __cplusplus
 }

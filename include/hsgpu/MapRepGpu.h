@@ -8,14 +8,14 @@
 //   mapRep = new MapRepGpu(mapResolution, mapSizeX, mapSizeY, multi_res_size, startCoords, drawInterfaceIn, debugInterfaceIn);
 //
 //   matchData     -> hs_match_batch   (MapRepMultiMap::matchData, coarse to fine; refreshes the coarse containers)
-//   updateByScan  -> hs_raycast_batch (MapRepMultiMap::updateByScan on all levels with the given pose)
+//   updateByScan  -> hs_integrate_batch (MapRepMultiMap::updateByScan: level 0 from the given scan, the coarse levels from
+//                    the containers the last matchData left behind, MapRepMultiMap.h:134-147)
 //   onMapUpdated  -> nothing to do    (there is no GridMapCacheArray to invalidate)
 //   getGridMap    -> lazily refreshed host mirror, as in hsgpu/HectorSlamProcessor.h
 //
-// One difference, by design: updateByScan integrates the coarse levels from the scan it is GIVEN (scaled by 2^-level,
-// MapRepMultiMap.h:127), not from the containers the last matchData left behind. The two are the same whenever
-// updateByScan follows matchData of the same scan -- which is what HectorSlamProcessor::update does (:84-93). A caller that
-// needs the reference's stale-container behaviour of update(..., map_without_matching = true) uses the processor façade.
+// As in the reference, updateByScan of a scan that was not the last one matched integrates STALE (or, before the first
+// matchData, empty) containers on the coarse levels -- e.g. HectorSlamProcessor::update(..., map_without_matching = true)
+// (tests/cpp/maprep_test.cpp drives exactly that against the CPU reference).
 // Needs Eigen exactly as the reference header does. No CPU fallback: the constructor throws without a CUDA device.
 #ifndef HSGPU_MAPREPGPU_H
 #define HSGPU_MAPREPGPU_H
@@ -115,9 +115,9 @@ class MapRepGpu : public MapRepresentationInterface {
       const float pose[3] = {robotPoseWorld[0], robotPoseWorld[1], robotPoseWorld[2]};
       std::lock_guard<std::mutex> guard(engine_mutex_);
       for (size_t i = 0; i < mutexes_.size(); ++i) if (mutexes_[i]) mutexes_[i]->lockMap();
-      int st = hs_raycast_batch(engine_, 1, 0, points_.data(), &count, origo, pose);
+      int st = hs_integrate_batch(engine_, 1, 0, points_.data(), &count, origo, pose);
       for (size_t i = 0; i < mutexes_.size(); ++i) if (mutexes_[i]) mutexes_[i]->unlockMap();
-      if (st != HS_OK) throw std::runtime_error(std::string("hsgpu: hs_raycast_batch failed: ") + hs_status_string(st));
+      if (st != HS_OK) throw std::runtime_error(std::string("hsgpu: hs_integrate_batch failed: ") + hs_status_string(st));
       int ui = -1;
       hs_get_update_index(engine_, 0, 0, &ui);
       for (size_t i = 0; i < levels_.size(); ++i) setLevelUpdateIndex(i, ui);

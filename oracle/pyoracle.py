@@ -199,6 +199,19 @@ class CpuProcessor:
         self.f["refresh_coarse"](self.h, points.ctypes.data, n, float(origo[0]), float(origo[1]))
         self.f["update_by_scan_all"](self.h, points.ctypes.data, n, float(origo[0]), float(origo[1]), pose_world.ctypes.data)
 
+    def refresh_coarse(self, points, n=None, origo=(0.0, 0.0)):
+        """MapRepMultiMap::matchData run for its side effect on dataContainers (MapRepMultiMap.h:127); pose discarded."""
+        points = _f32(points)
+        n = points.reshape(-1, 2).shape[0] if n is None else int(n)
+        self.f["refresh_coarse"](self.h, points.ctypes.data, n, float(origo[0]), float(origo[1]))
+
+    def integrate(self, points, pose_world, n=None, origo=(0.0, 0.0)):
+        """MapRepMultiMap::updateByScan + onMapUpdated (MapRepMultiMap.h:134-147): the coarse levels use whatever the last
+        matchData left in dataContainers."""
+        points = _f32(points); pose_world = _f32(pose_world)
+        n = points.reshape(-1, 2).shape[0] if n is None else int(n)
+        self.f["update_by_scan_all"](self.h, points.ctypes.data, n, float(origo[0]), float(origo[1]), pose_world.ctypes.data)
+
     # off-path OccGridMapUtil members (OccGridMapUtil.h:106-285); poses in MAP coordinates, points scaled to the level
     def interp_map_value(self, level, x, y): return float(self.f["interp_map_value"](self.h, level, float(x), float(y)))
 

@@ -2,7 +2,10 @@
 // reference's HectorSlamProcessor::update drives MapRepMultiMap (HectorSlamProcessor.h:71-95): matchData from the last pose,
 // the poseDifferenceLargerThan gate, updateByScan + onMapUpdated -- the gate and the bookkeeping are host code here, as in
 // the reference. Dumps poses, covariances and the final level cells for comparison with the CPU oracle.
-// usage: maprep_test <in.bin> <out.bin>      (formats as facade_test.cpp; gate thresholds 0.4 m / 0.9 rad)
+// usage: maprep_test <in.bin> <out.bin> [mwm_period]   (formats as facade_test.cpp; gate thresholds 0.4 m / 0.9 rad)
+// mwm_period P > 0: every scan k with k % P == P - 1 takes update()'s map_without_matching = true branch
+// (HectorSlamProcessor.h:78-82, :89): no matchData, the pose hint becomes the pose, updateByScan runs unconditionally -- so
+// the coarse levels integrate the containers the LAST matched scan left behind (MapRepMultiMap.h:134-147).
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -27,6 +30,7 @@ int main(int argc, char** argv) {
   FILE* fi = std::fopen(argv[1], "rb");
   FILE* fo = std::fopen(argv[2], "wb");
   if (!fi || !fo) return 3;
+  const int mwm_period = argc > 3 ? std::atoi(argv[3]) : 0;
   int n_scans = 0, max_pts = 0;
   if (std::fread(&n_scans, 4, 1, fi) != 1 || std::fread(&max_pts, 4, 1, fi) != 1) return 4;
   hectorslam::MapRepresentationInterface* mapRep = new hectorslam::MapRepGpu(0.05f, 1024, 1024, 3, Eigen::Vector2f(0.5f, 0.5f), 0, 0);
@@ -46,9 +50,13 @@ int main(int argc, char** argv) {
     dc.clear();
     dc.setOrigo(Eigen::Vector2f::Zero());
     for (int i = 0; i < count; ++i) dc.add(Eigen::Vector2f(buf[2 * i], buf[2 * i + 1]));
-    const Eigen::Vector3f newPoseEstimateWorld = mapRep->matchData(lastScanMatchPose, dc, lastScanMatchCov);
+    const bool map_without_matching = mwm_period > 0 && (k % mwm_period) == mwm_period - 1;
+    const Eigen::Vector3f poseHintWorld = lastScanMatchPose;
+    Eigen::Vector3f newPoseEstimateWorld;
+    if (!map_without_matching) newPoseEstimateWorld = mapRep->matchData(poseHintWorld, dc, lastScanMatchCov);
+    else newPoseEstimateWorld = poseHintWorld;
     lastScanMatchPose = newPoseEstimateWorld;
-    if (pose_difference_larger_than(newPoseEstimateWorld, lastMapUpdatePose, 0.4f, 0.9f)) {
+    if (pose_difference_larger_than(newPoseEstimateWorld, lastMapUpdatePose, 0.4f, 0.9f) || map_without_matching) {
       mapRep->updateByScan(dc, newPoseEstimateWorld);
       mapRep->onMapUpdated();
       lastMapUpdatePose = newPoseEstimateWorld;

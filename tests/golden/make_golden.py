@@ -19,7 +19,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 
-import tfe_slam_ucl_b200 as hs  # noqa: E402  (host-side scan generator only)
+import workload  # noqa: E402  (host-side scan generator + conversion only: no CUDA library is loaded)
 from oracle import pyoracle  # noqa: E402
 
 
@@ -51,25 +51,25 @@ def main():
 
     cases = {
         # BASELINE configs[0]/[1] geometry: RPLidar-style 360-beam scans, 3 levels 1024^2 @0.05 m, ROS-node parameters
-        "c1_node_params": dict(preset=hs.SCENE_RPLIDAR_ROOM, seed=0xC0FFEE, n_scans=40, cfg=dict(res=0.05, size=1024, levels=3),
+        "c1_node_params": dict(preset=workload.SCENE_RPLIDAR_ROOM, seed=0xC0FFEE, n_scans=40, cfg=dict(res=0.05, size=1024, levels=3),
                                params=dict(free=0.4, occ=0.9, dist=0.4, ang=0.9), mwm_every=0),
         # every scan integrated (gate 0/0), library-default factors 0.4/0.6, with map_without_matching every 7th scan
-        "c1_gate0_mwm": dict(preset=hs.SCENE_RPLIDAR_ROOM, seed=0xC0FFEE + 1, n_scans=30, cfg=dict(res=0.05, size=1024, levels=3),
+        "c1_gate0_mwm": dict(preset=workload.SCENE_RPLIDAR_ROOM, seed=0xC0FFEE + 1, n_scans=30, cfg=dict(res=0.05, size=1024, levels=3),
                              params=dict(free=0.4, occ=0.6, dist=0.0, ang=0.0), mwm_every=7),
         # BASELINE configs[2] shape, reduced: 1440-beam 30 m scans, 4 levels 2048^2 @0.025 m
-        "c3_small": dict(preset=hs.SCENE_HIRES_HALL, seed=0xC0FFEE + 2, n_scans=8, cfg=dict(res=0.025, size=2048, levels=4),
+        "c3_small": dict(preset=workload.SCENE_HIRES_HALL, seed=0xC0FFEE + 2, n_scans=8, cfg=dict(res=0.025, size=2048, levels=4),
                          params=dict(free=0.4, occ=0.9, dist=0.0, ang=0.0), mwm_every=0),
     }
     for name, c in cases.items():
-        sc = hs.scene_preset(c["preset"])
-        ranges, _ = hs.scangen_batch(sc, c["seed"], 1, 0, c["n_scans"], truth=False)
+        sc = workload.scene_preset(c["preset"])
+        ranges, _ = workload.scangen_batch(sc, c["seed"], 1, 0, c["n_scans"], truth=False)
         ranges = ranges[:, 0]
         if name == "c1_gate0_mwm":   # ragged input: knock out ranges so that counts vary, plus one empty scan
             rng = np.random.default_rng(5)
             mask = rng.random(ranges.shape) < 0.15
             ranges = ranges.copy(); ranges[mask] = np.inf
             ranges[11, :] = 0.05     # below range_min: DataContainer stays empty
-        pts, cnt = hs.scan_to_points_host(ranges, sc, 1.0 / c["cfg"]["res"])
+        pts, cnt = workload.scan_to_points_host(ranges, sc, 1.0 / c["cfg"]["res"])
         p, poses, covs, upd, digests = run_stream("ref", c["cfg"], pts, cnt, c["params"], c["mwm_every"])
         arrays[name + "/points"] = pts; arrays[name + "/counts"] = cnt
         arrays[name + "/poses"] = poses; arrays[name + "/cov"] = covs; arrays[name + "/update_index"] = upd

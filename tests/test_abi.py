@@ -3,6 +3,7 @@ include/hsgpu.h declares, keeps the LogOddsCell layout, and fails loudly (no CPU
 import ctypes
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -23,7 +24,7 @@ def test_header_declares_expected_surface():
                  "hs_hessian_derivs_batch", "hs_raycast_batch", "hs_match_batch", "hs_download_level", "hs_upload_level",
                  "hs_get_poses", "hs_get_covariances", "hs_set_update_factor_free", "hs_set_update_factor_occupied",
                  "hs_set_map_update_min_dist_diff", "hs_set_map_update_min_angle_diff", "hs_get_scale_to_map", "hs_get_map_levels",
-                 "hs_classify_level", "hs_get_update_index", "hs_status_string", "hs_scangen_batch", "hs_scan_to_points_host"]:
+                 "hs_classify_level", "hs_get_update_index", "hs_status_string", "hs_integrate_batch", "hs_scan_to_points_host"]:
         assert must in names, must
     assert len(names) >= 35
 
@@ -75,3 +76,21 @@ def test_product_does_not_link_the_oracle(hs):
         for fn in files:
             if fn.endswith((".py", ".cu", ".cuh", ".c", ".h")):
                 assert "oracle" not in open(os.path.join(root, fn)).read().replace("no oracle", ""), fn
+
+
+def test_product_library_holds_no_workload_generator(hs):
+    """The synthetic scan generator lives in workload/libhsscangen.so (include/hsscangen.h), not in the product; the CPU-only
+    arms (bench.py --impl reference, golden generation, the gloo test) load it without mapping libhsgpu.so."""
+    import subprocess
+    import workload
+    out = subprocess.run(["nm", "-D", hs.LIB_PATH], capture_output=True, text=True).stdout
+    assert "hs_scangen_batch" not in out and "hs_scene_preset" not in out
+    wl = subprocess.run(["nm", "-D", workload.lib() and workload.LIB_PATH], capture_output=True, text=True).stdout
+    assert "hs_scangen_batch" in wl and "hs_scan_to_points_host_batch" in wl
+    ldd = subprocess.run(["ldd", workload.LIB_PATH], capture_output=True, text=True).stdout
+    assert "cuda" not in ldd.lower() and "hsgpu" not in ldd
+    code = ("import sys; sys.path.insert(0, %r); import workload; sc = workload.scene_preset(0); "
+            "r, _ = workload.scangen_batch(sc, 1, 1, 0, 1, truth=False); p, c = workload.scan_to_points_host(r, sc, 20.0); "
+            "maps = open('/proc/self/maps').read(); assert 'libhsgpu' not in maps and 'libcudart' not in maps; print(int(c.sum()))" % ROOT)
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert res.returncode == 0 and int(res.stdout.strip()) > 100, res.stderr

@@ -175,3 +175,37 @@ def test_maprep_gpu_matches_oracle(tmp_path, hs, oracle):
         ref = p.download_level(l)
         assert (sx, sy) == p.level_dims(l)[:2] and ui == p.update_index(l)
         assert np.array_equal(cells["updateIndex"], ref["updateIndex"]) and np.array_equal(bits(cells["logOddsVal"]), bits(ref["logOddsVal"]))
+
+
+@pytest.mark.gpu
+def test_maprep_gpu_map_without_matching_integrates_stale_containers(tmp_path, hs, oracle):
+    """The reference's HectorSlamProcessor::update(..., map_without_matching = true) on top of MapRepGpu: updateByScan of a scan
+    that was NOT matched integrates, on the coarse levels, the containers the last matchData left behind
+    (MapRepMultiMap.h:134-147). Checked against the reference itself (oracle/_ref) when present, else its C restatement."""
+    exe = build_maprep_test(tmp_path, hs)
+    n_scans, mp, period = 60, 360, 3
+    sc, ranges, pts, cnt, truth = make_streams(hs, 1, n_scans, seed0=1717)
+    with open(tmp_path / "in.bin", "wb") as f:
+        f.write(np.array([n_scans, mp], np.int32).tobytes())
+        for k in range(n_scans):
+            f.write(np.array([cnt[k, 0]], np.int32).tobytes())
+            f.write(pts[k, 0].astype(np.float32).tobytes())
+    res = subprocess.run([exe, str(tmp_path / "in.bin"), str(tmp_path / "out.bin"), str(period)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    raw = open(tmp_path / "out.bin", "rb").read()
+    rows = np.frombuffer(raw[: n_scans * 48], np.float32).reshape(n_scans, 12)
+    p = oracle.CpuProcessor("ref" if oracle.have("ref") else "port")
+    p.set_update_factor_free(0.4); p.set_update_factor_occupied(0.9)
+    p.set_map_update_min_dist_diff(0.4); p.set_map_update_min_angle_diff(0.9)
+    for k in range(n_scans):
+        pose = p.update(pts[k, 0], cnt[k, 0], hint=p.pose(), map_without_matching=(k % period == period - 1))
+        assert np.array_equal(bits(rows[k, :3]), bits(pose)), k
+    off = n_scans * 48
+    for l in range(3):
+        sx, sy, ui = np.frombuffer(raw[off: off + 12], np.int32)
+        off += 12
+        cells = np.frombuffer(raw[off: off + sx * sy * 8], oracle.CELL_DTYPE)
+        off += sx * sy * 8
+        ref = p.download_level(l)
+        assert ui == p.update_index(l)
+        assert np.array_equal(cells["updateIndex"], ref["updateIndex"]) and np.array_equal(bits(cells["logOddsVal"]), bits(ref["logOddsVal"])), l

@@ -100,6 +100,16 @@ def test_stream_ids_subset_and_permutation(hs, oracle):
         assert not eng.poses(untouched, 1).any()
     with pytest.raises(hs.HsError):
         eng.update_batch(pts[0], cnt[0], stream_ids=np.array([0, 1, 6], np.int32))
+    # duplicate ids would put two CTAs on one stream's maps and counters: refused by every host entry point, state untouched
+    before = eng.poses()
+    dup = np.array([2, 5, 2], np.int32)
+    for call in (lambda: eng.update_batch(pts[0], cnt[0], stream_ids=dup), lambda: eng.match_batch(pts[0], cnt[0], stream_ids=dup),
+                 lambda: eng.raycast_batch(pts[0], cnt[0], truth[0], stream_ids=dup),
+                 lambda: eng.raycast_batch(pts[0], cnt[0], truth[0], stream_ids=dup, refresh_coarse=False)):
+        with pytest.raises(hs.HsError) as err:
+            call()
+        assert err.value.status == hs.HS_ERR_INVALID_ARG
+    assert np.array_equal(bits(before), bits(eng.poses()))
     eng.close()
 
 

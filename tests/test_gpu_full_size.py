@@ -7,6 +7,7 @@ Properties: streams are independent (a stream's result does not depend on what e
 slot), untouched streams stay pristine, integrations/cell-visit counters add up, update indices advance by one per
 integrated scan."""
 import numpy as np
+import workload
 import pytest
 
 from hs_testutil import bits, make_streams
@@ -60,14 +61,14 @@ def run_config(hs, oracle, n_streams, n_scans, preset, size, levels, res, max_po
 def test_config1_1024_streams(hs, oracle):
     rng = np.random.default_rng(0)
     sample = sorted(rng.choice(1024, 12, replace=False).tolist())
-    st, _ = run_config(hs, oracle, 1024, 6, hs.SCENE_RPLIDAR_ROOM, 1024, 3, 0.05, 360, sample)
+    st, _ = run_config(hs, oracle, 1024, 6, workload.SCENE_RPLIDAR_ROOM, 1024, 3, 0.05, 360, sample)
     assert st["cell_visits"] > 1024 * 5 * 30000
 
 
 def test_config2_hires_256_streams(hs, oracle):
-    st, _ = run_config(hs, oracle, 256, 3, hs.SCENE_HIRES_HALL, 4096, 4, 0.025, 1440, [0, 131, 255])
+    st, _ = run_config(hs, oracle, 256, 3, workload.SCENE_HIRES_HALL, 4096, 4, 0.025, 1440, [0, 131, 255])
     assert st["kernel_launches"] > 0
 
 
 def test_config4_8192_streams_one_gpu(hs, oracle):
-    run_config(hs, oracle, 8192, 3, hs.SCENE_RPLIDAR_ROOM, 1024, 3, 0.05, 360, [0, 4097, 8191], gate=(0.4, 0.9))
+    run_config(hs, oracle, 8192, 3, workload.SCENE_RPLIDAR_ROOM, 1024, 3, 0.05, 360, [0, 4097, 8191], gate=(0.4, 0.9))

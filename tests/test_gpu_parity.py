@@ -92,6 +92,60 @@ def test_raycast_teacher_forced_bitexact(hs, oracle):
             assert eng.update_index(s, 0) == p.update_index(0) == n_scans - 1
 
 
+def test_integrate_uses_the_containers_of_the_last_match(hs, oracle):
+    """hs_integrate_batch = MapRepMultiMap::updateByScan proper (MapRepMultiMap.h:134-147): match scan A, integrate scan B ->
+    level 0 gets B, the coarse levels get A (stale); before any match they get nothing. Against the reference itself
+    (oracle/_ref) when it is on the box. hs_raycast_batch (teacher forcing) refreshes the containers and must differ."""
+    kind = "ref" if oracle.have("ref") else "port"
+    n = 3
+    sc, ranges, pts, cnt, truth = make_streams(hs, n, 12, seed0=5150)
+    procs = [oracle.CpuProcessor(kind) for _ in range(n)]
+    for p in procs:
+        configure(p, **NODE)
+    with hs.Engine(n_streams=n, max_points=360) as eng, hs.Engine(n_streams=n, max_points=360) as eng_tf:
+        configure(eng, **NODE); configure(eng_tf, **NODE)
+        # no match yet: the coarse containers are empty, only level 0 is integrated
+        for s, p in enumerate(procs):
+            p.integrate(pts[0, s], truth[0, s], cnt[0, s])
+        eng.raycast_batch(pts[0], cnt[0], truth[0], refresh_coarse=False)
+        eng_tf.raycast_batch(pts[0], cnt[0], truth[0])
+        for k in range(1, 11, 2):
+            hint = truth[k]
+            for s, p in enumerate(procs):
+                p.refresh_coarse(pts[k, s], cnt[k, s])               # matchData of scan k (pose discarded)
+                p.integrate(pts[k + 1, s], truth[k + 1, s], cnt[k + 1, s])   # updateByScan of scan k+1
+            eng.match_batch(pts[k], cnt[k], pose_hints=hint)
+            eng.raycast_batch(pts[k + 1], cnt[k + 1], truth[k + 1], refresh_coarse=False)
+            eng_tf.raycast_batch(pts[k + 1], cnt[k + 1], truth[k + 1])
+        n_diff, _ = compare_maps(eng, procs, 3, exact=True)
+        assert n_diff == 0
+        coarse_differs = any(not np.array_equal(eng.download_level(s, l)["updateIndex"], eng_tf.download_level(s, l)["updateIndex"])
+                             for s in range(n) for l in (1, 2))
+        assert coarse_differs, "the stale-container path must be distinguishable from teacher forcing"
+        assert all(np.array_equal(eng.download_level(s, 0)["updateIndex"], eng_tf.download_level(s, 0)["updateIndex"]) for s in range(n))
+
+
+def test_short_stream_against_the_reference_itself(hs, oracle):
+    """Closes the chain on the GPU box: the CUDA path against oracle/_ref (the unmodified reference headers) directly, not via
+    the C restatement. Skipped only where _ref was never built."""
+    if not oracle.have("ref"):
+        pytest.skip("oracle/_ref not built on this box")
+    n_streams, n_scans = 4, 60
+    sc, ranges, pts, cnt, truth = make_streams(hs, n_streams, n_scans, seed0=2468)
+    procs = [oracle.CpuProcessor("ref") for _ in range(n_streams)]
+    for p in procs:
+        configure(p, **NODE)
+    _, cpu_poses, cpu_cov = oracle.run_streams(procs, pts, cnt, threads=2, want_cov=True)
+    with hs.Engine(n_streams=n_streams, max_points=360) as eng:
+        configure(eng, **NODE)
+        for k in range(n_scans):
+            poses, cov = eng.update_batch(pts[k], cnt[k])
+            assert np.array_equal(bits(poses), bits(cpu_poses[k])), k
+            assert np.array_equal(bits(cov.reshape(n_streams, 9)), bits(cpu_cov[k])), k
+        n_diff, _ = compare_maps(eng, procs, 3, exact=True)
+        assert n_diff == 0
+
+
 def test_closed_loop_strict_bitexact(hs, oracle):
     """Full update() loop, strict summation: poses, covariances and maps equal the oracle bit for bit."""
     n_streams, n_scans = 8, 120

@@ -2,32 +2,33 @@
 conversion (hs_scan_to_points_host, the host twin of k_scan_to_points) equals the oracle's restatement of
 HectorMappingRos::rosLaserScanToDataContainer (HectorMappingRos.cpp:483-507), including the range window."""
 import numpy as np
+import workload
 
 from hs_testutil import bits
 
 
 def test_scangen_is_deterministic_and_random_access(hs):
-    sc = hs.scene_preset(hs.SCENE_RPLIDAR_ROOM)
-    a, ta = hs.scangen_batch(sc, 77, 3, 0, 6, threads=1)
-    b, tb = hs.scangen_batch(sc, 77, 3, 0, 6, threads=4)
+    sc = workload.scene_preset(workload.SCENE_RPLIDAR_ROOM)
+    a, ta = workload.scangen_batch(sc, 77, 3, 0, 6, threads=1)
+    b, tb = workload.scangen_batch(sc, 77, 3, 0, 6, threads=4)
     assert np.array_equal(bits(a), bits(b)) and np.array_equal(bits(ta), bits(tb))
-    c, _ = hs.scangen_batch(sc, 77, 3, 4, 2)          # scans 4,5 generated on their own
+    c, _ = workload.scangen_batch(sc, 77, 3, 4, 2)          # scans 4,5 generated on their own
     assert np.array_equal(bits(a[4:6]), bits(c))
-    d, _ = hs.scangen_batch(sc, 78, 2, 0, 6)           # stream seed0+1 of the first batch == stream 0 here
+    d, _ = workload.scangen_batch(sc, 78, 2, 0, 6)           # stream seed0+1 of the first batch == stream 0 here
     assert np.array_equal(bits(a[:, 1:3]), bits(d))
     assert a.shape == (6, 3, 360) and np.isfinite(a).mean() > 0.95
     assert 0.2 < a[np.isfinite(a)].min() and a[np.isfinite(a)].max() < 12.9
     # smooth trajectory: <= 0.05 m and <= 0.03 rad per scan (SURVEY 8(d))
     step = np.abs(np.diff(ta, axis=0))
     assert step[..., :2].max() < 0.05 and step[..., 2].max() < 0.03
-    hall = hs.scene_preset(hs.SCENE_HIRES_HALL)
-    r, _ = hs.scangen_batch(hall, 5, 1, 0, 1)
+    hall = workload.scene_preset(workload.SCENE_HIRES_HALL)
+    r, _ = workload.scangen_batch(hall, 5, 1, 0, 1)
     assert r.shape == (1, 1, 1440)
 
 
 def test_scan_to_points_matches_oracle_restatement(hs, oracle):
-    sc = hs.scene_preset(hs.SCENE_RPLIDAR_ROOM)
-    ranges, _ = hs.scangen_batch(sc, 3, 2, 0, 4)
+    sc = workload.scene_preset(workload.SCENE_RPLIDAR_ROOM)
+    ranges, _ = workload.scangen_batch(sc, 3, 2, 0, 4)
     ranges = ranges.reshape(-1, 360).copy()
     rng = np.random.default_rng(0)
     ranges[0, ::7] = np.inf                 # dropped: >= range_max - 0.1

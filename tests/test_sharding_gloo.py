@@ -12,6 +12,9 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+import workload  # noqa: E402
 
 
 def _free_port():
@@ -27,13 +30,12 @@ def _worker(rank, world, port, n_total, n_scans, out_dir):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    import tfe_slam_ucl_b200 as hs
-    from tfe_slam_ucl_b200 import sharding
+    from tfe_slam_ucl_b200 import sharding          # host logic only: libhsgpu.so is never mapped here
     from oracle import pyoracle
     first, count = sharding.shard_range(n_total, world, rank)
-    sc = hs.scene_preset(hs.SCENE_RPLIDAR_ROOM)
-    ranges, _ = hs.scangen_batch(sc, 4000 + first, count, 0, n_scans, threads=1, truth=False)
-    pts, cnt = hs.scan_to_points_host(ranges, sc, 20.0)
+    sc = workload.scene_preset(workload.SCENE_RPLIDAR_ROOM)
+    ranges, _ = workload.scangen_batch(sc, 4000 + first, count, 0, n_scans, threads=1, truth=False)
+    pts, cnt = workload.scan_to_points_host(ranges, sc, 20.0)
     procs = [pyoracle.CpuProcessor("port", 0.05, 256, 256, (0.5, 0.5), 2) for _ in range(count)]
     secs, poses, _ = pyoracle.run_streams(procs, pts, cnt, threads=1)
     local_seconds = 1.0 + rank              # deterministic stand-in for the device timer
@@ -73,11 +75,10 @@ def test_two_rank_gloo_sharded_run_matches_unsharded(tmp_path):
     gathered = np.load(tmp_path / "gathered.npy")
     # unsharded reference run in this process
     sys.path.insert(0, ROOT)
-    import tfe_slam_ucl_b200 as hs
     from oracle import pyoracle
-    sc = hs.scene_preset(hs.SCENE_RPLIDAR_ROOM)
-    ranges, _ = hs.scangen_batch(sc, 4000, n_total, 0, n_scans, threads=1, truth=False)
-    pts, cnt = hs.scan_to_points_host(ranges, sc, 20.0)
+    sc = workload.scene_preset(workload.SCENE_RPLIDAR_ROOM)
+    ranges, _ = workload.scangen_batch(sc, 4000, n_total, 0, n_scans, threads=1, truth=False)
+    pts, cnt = workload.scan_to_points_host(ranges, sc, 20.0)
     procs = [pyoracle.CpuProcessor("port", 0.05, 256, 256, (0.5, 0.5), 2) for _ in range(n_total)]
     _, poses, _ = pyoracle.run_streams(procs, pts, cnt, threads=2)
     assert gathered.shape == (n_total, 3)

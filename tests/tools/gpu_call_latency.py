@@ -6,10 +6,11 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import tfe_slam_ucl_b200 as hs
+import workload
 
 S, K, W = 1024, 100, 5
-sc = hs.scene_preset(0)
-ranges, _ = hs.scangen_batch(sc, 0xC0FFEE, S, 0, K + W, truth=False)
+sc = workload.scene_preset(0)
+ranges, _ = workload.scangen_batch(sc, 0xC0FFEE, S, 0, K + W, truth=False)
 pts, cnt = hs.scan_to_points_host(ranges, sc, 20.0)
 h_pts = torch.from_numpy(pts).pin_memory(); h_cnt = torch.from_numpy(cnt).pin_memory()
 h_pose = torch.empty((S, 3), dtype=torch.float32).pin_memory()

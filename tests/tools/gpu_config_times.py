@@ -7,14 +7,15 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import tfe_slam_ucl_b200 as hs
+import workload
 
 K = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 W = 3
 
 def hires():
     S, res, size, levels, mp = 256, 0.025, 4096, 4, 1440
-    sc = hs.scene_preset(hs.SCENE_HIRES_HALL)
-    ranges, _ = hs.scangen_batch(sc, 0xC0FFEE, S, 0, K + W, truth=False)
+    sc = workload.scene_preset(workload.SCENE_HIRES_HALL)
+    ranges, _ = workload.scangen_batch(sc, 0xC0FFEE, S, 0, K + W, truth=False)
     pts, cnt = hs.scan_to_points_host(ranges, sc, 1.0 / res)
     with hs.Engine(res, size, size, (0.5, 0.5), levels, n_streams=S, max_points=mp) as eng:
         eng.set_update_factor_free(0.4); eng.set_update_factor_occupied(0.9)
@@ -39,8 +40,8 @@ def hires():
                           "cell_visits_per_scan": visits, "mean_points": float(cnt.mean())}))
 
 def hypotheses():
-    sc = hs.scene_preset(hs.SCENE_RPLIDAR_ROOM)
-    ranges, truth = hs.scangen_batch(sc, 0xC0FFEE, 1, 0, 201, truth=True)
+    sc = workload.scene_preset(workload.SCENE_RPLIDAR_ROOM)
+    ranges, truth = workload.scangen_batch(sc, 0xC0FFEE, 1, 0, 201, truth=True)
     pts, cnt = hs.scan_to_points_host(ranges, sc, 20.0)
     with hs.Engine(n_streams=1, max_points=360) as eng:
         eng.set_update_factor_free(0.4); eng.set_update_factor_occupied(0.9)

@@ -6,12 +6,13 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import tfe_slam_ucl_b200 as hs
+import workload
 
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 K = int(sys.argv[2]) if len(sys.argv) > 2 else 30
 W = 3
-sc = hs.scene_preset(0)
-ranges, _ = hs.scangen_batch(sc, 0xC0FFEE, S, 0, K + W, truth=False)
+sc = workload.scene_preset(0)
+ranges, _ = workload.scangen_batch(sc, 0xC0FFEE, S, 0, K + W, truth=False)
 pts, cnt = hs.scan_to_points_host(ranges, sc, 20.0)
 for E in (1, 2, 4):
     per = S // E

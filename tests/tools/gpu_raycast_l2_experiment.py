@@ -6,10 +6,11 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import tfe_slam_ucl_b200 as hs
+import workload
 
 S, K = 1024, 30
-sc = hs.scene_preset(0)
-ranges, _ = hs.scangen_batch(sc, 0xC0FFEE, S, 0, K, truth=False)
+sc = workload.scene_preset(0)
+ranges, _ = workload.scangen_batch(sc, 0xC0FFEE, S, 0, K, truth=False)
 pts, cnt = hs.scan_to_points_host(ranges, sc, 20.0)
 os.environ.pop("HSGPU_DEBUG_SKIP", None)
 with hs.Engine(n_streams=S, max_points=360) as eng:

@@ -8,11 +8,12 @@ out = os.path.join(ROOT, "gpurun_out", "raycast_times.bin")
 os.environ["HSGPU_DEBUG_TIMES"] = out
 import torch
 import tfe_slam_ucl_b200 as hs
+import workload
 
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 K = int(sys.argv[2]) if len(sys.argv) > 2 else 30
-sc = hs.scene_preset(0)
-ranges, _ = hs.scangen_batch(sc, 0xC0FFEE, S, 0, K, truth=False)
+sc = workload.scene_preset(0)
+ranges, _ = workload.scangen_batch(sc, 0xC0FFEE, S, 0, K, truth=False)
 pts, cnt = hs.scan_to_points_host(ranges, sc, 20.0)
 eng = hs.Engine(n_streams=S, max_points=360)
 eng.set_update_factor_free(0.4); eng.set_update_factor_occupied(0.9)

@@ -7,11 +7,12 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import tfe_slam_ucl_b200 as hs
+import workload
 
 def run(variant, size, res, levels, preset, mp, n=3, scans=3):
     os.environ["HSGPU_MATCH_VARIANT"] = variant
-    sc = hs.scene_preset(preset)
-    ranges, _ = hs.scangen_batch(sc, 77, n, 0, scans, truth=False)
+    sc = workload.scene_preset(preset)
+    ranges, _ = workload.scangen_batch(sc, 77, n, 0, scans, truth=False)
     pts, cnt = hs.scan_to_points_host(ranges, sc, 1.0 / res)
     with hs.Engine(res, size, size, (0.5, 0.5), levels, n_streams=n, max_points=mp) as eng:
         eng.set_update_factor_free(0.4); eng.set_update_factor_occupied(0.9)
@@ -32,6 +33,6 @@ def run(variant, size, res, levels, preset, mp, n=3, scans=3):
         eng.update_batch_clouds(clouds, np.full(n, 64, np.int32), xf, 0.16, 900.0, -1.0, 1.0)
         print("ok", variant, size, eng.stats()["kernel_launches"])
 
-run("1", 1024, 0.05, 3, hs.SCENE_RPLIDAR_ROOM, 360)
-run("2", 1024, 0.05, 3, hs.SCENE_RPLIDAR_ROOM, 360)
-run("2", 2048, 0.025, 3, hs.SCENE_HIRES_HALL, 1440, n=3, scans=2)     # banded ray-cast
+run("1", 1024, 0.05, 3, workload.SCENE_RPLIDAR_ROOM, 360)
+run("2", 1024, 0.05, 3, workload.SCENE_RPLIDAR_ROOM, 360)
+run("2", 2048, 0.025, 3, workload.SCENE_HIRES_HALL, 1440, n=3, scans=2)     # banded ray-cast

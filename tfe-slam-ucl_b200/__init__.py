@@ -24,8 +24,6 @@ HS_ERR_NO_DEVICE = -2
 HS_ERR_OUT_OF_MEMORY = -3
 HS_ERR_NOT_CONFIGURED = -4
 HS_ALL_STREAMS = -1
-SCENE_RPLIDAR_ROOM = 0
-SCENE_HIRES_HALL = 1
 
 CELL_DTYPE = np.dtype([("logOddsVal", np.float32), ("updateIndex", np.int32)])
 
@@ -64,14 +62,6 @@ class HsKernelTimes(ctypes.Structure):
 
 
 KERNEL_NAMES = ("k_scan_to_points", "k_match", "k_raycast")
-
-
-class SceneConfig(ctypes.Structure):
-    _fields_ = [("n_beams", ctypes.c_int32), ("angle_min", ctypes.c_float), ("angle_increment", ctypes.c_float),
-                ("range_min", ctypes.c_float), ("range_max", ctypes.c_float), ("noise_sigma", ctypes.c_float),
-                ("room_w", ctypes.c_float), ("room_h", ctypes.c_float), ("n_boxes", ctypes.c_int32),
-                ("box_min", ctypes.c_float), ("box_max", ctypes.c_float), ("traj_rx", ctypes.c_float),
-                ("traj_ry", ctypes.c_float), ("traj_period", ctypes.c_int32)]
 
 
 def build(verbose=False):
@@ -122,6 +112,7 @@ def lib():
         "hs_match_batch": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _P]),
         "hs_match_hypotheses": (_I, [_P, _I, _P, _I, _P, _I, _P, _P]),
         "hs_raycast_batch": (_I, [_P, _I, _P, _P, _P, _P, _P]),
+        "hs_integrate_batch": (_I, [_P, _I, _P, _P, _P, _P, _P]),
         "hs_download_level": (_I, [_P, _I, _I, _P]), "hs_upload_level": (_I, [_P, _I, _I, _P]),
         "hs_get_update_index": (_I, [_P, _I, _I, _P]), "hs_classify_level": (_I, [_P, _I, _I, _P]),
         "hs_get_stats": (_I, [_P, _P]), "hs_get_map_info": (_I, [_P, _I, _P]),
@@ -133,8 +124,6 @@ def lib():
         "hs_occupancy_ray_batch": (_I, [_P, _I, _I, _P, _P, _I, _P, _P]),
         "hs_export_stream_state": (_I, [_P, _I, _P, _P]), "hs_import_stream_state": (_I, [_P, _I, _P, _P]),
         "hs_profile_enable": (_I, [_P, _I]), "hs_profile_collect": (_I, [_P, _P]),
-        "hs_scene_preset": (_I, [_I, _P]),
-        "hs_scangen_batch": (_I, [_P, ctypes.c_uint64, _I, _I, _I, _P, _P, _I]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -166,26 +155,11 @@ def _ptr(a):
     return None if a is None else a.ctypes.data
 
 
-# ---- synthetic scan streams (host) -----------------------------------------------------------------
-
-def scene_preset(preset=SCENE_RPLIDAR_ROOM):
-    sc = SceneConfig()
-    _check(lib().hs_scene_preset(preset, ctypes.byref(sc)), "hs_scene_preset")
-    return sc
-
-
-def scangen_batch(scene, seed0, n_streams, first_scan, n_scans, threads=None, truth=True, out=None):
-    """ranges [n_scans][n_streams][n_beams] (and truth poses [n_scans][n_streams][3])."""
-    threads = threads or (os.cpu_count() or 1)
-    ranges = out if out is not None else np.empty((n_scans, n_streams, scene.n_beams), np.float32)
-    tr = np.empty((n_scans, n_streams, 3), np.float32) if truth else None
-    _check(lib().hs_scangen_batch(ctypes.byref(scene), seed0, n_streams, first_scan, n_scans, ranges.ctypes.data,
-                                  _ptr(tr), threads), "hs_scangen_batch")
-    return ranges, tr
-
+# ---- host twins of the ingestion kernels --------------------------------------------------------------
 
 def scan_to_points_host(ranges, scene, scale_to_map, max_points=None):
-    """rosLaserScanToDataContainer over a [..., n_beams] array -> (points [..., max_points, 2], counts [...])."""
+    """rosLaserScanToDataContainer over a [..., n_beams] array -> (points [..., max_points, 2], counts [...]).
+    `scene`: anything with angle_min / angle_increment / range_min / range_max (the LaserScan header fields)."""
     ranges = np.ascontiguousarray(ranges, np.float32)
     lead = ranges.shape[:-1]
     nb = ranges.shape[-1]
@@ -358,15 +332,17 @@ class Engine:
                                          poses.ctypes.data, cov.ctypes.data), "hs_match_hypotheses")
         return poses, cov.reshape(n, 3, 3)
 
-    def raycast_batch(self, points, counts, poses_world, origos=None, stream_ids=None):
+    def raycast_batch(self, points, counts, poses_world, origos=None, stream_ids=None, refresh_coarse=True):
+        """refresh_coarse=True: hs_raycast_batch (teacher forcing); False: hs_integrate_batch (MapRepMultiMap::updateByScan
+        proper: the coarse levels integrate the containers the last matchData left behind)."""
         counts = _arr(counts, np.int32)
         n = counts.shape[0]
         points = _arr(points, np.float32, (n, self.max_points, 2))
         origos = _arr(origos, np.float32, (n, 2))
         poses_world = _arr(poses_world, np.float32, (n, 3))
         ids = _arr(stream_ids, np.int32, (n,))
-        _check(lib().hs_raycast_batch(self._h, n, _ptr(ids), points.ctypes.data, counts.ctypes.data, _ptr(origos),
-                                      poses_world.ctypes.data), "hs_raycast_batch")
+        fn, name = (lib().hs_raycast_batch, "hs_raycast_batch") if refresh_coarse else (lib().hs_integrate_batch, "hs_integrate_batch")
+        _check(fn(self._h, n, _ptr(ids), points.ctypes.data, counts.ctypes.data, _ptr(origos), poses_world.ctypes.data), name)
 
     def hessian_derivs_batch(self, stream, level, poses_map, points):
         poses_map = _arr(poses_map, np.float32).reshape(-1, 3)

@@ -62,6 +62,7 @@ struct hs_engine {
   std::vector<cudaEvent_t>* prof_events;  // pairs: start, stop
   std::vector<int>* prof_ids;
   size_t prof_used;
+  std::vector<uint64_t>* id_bitmap;        // check_ids scratch
 };
 
 enum { HS_K_SCAN_TO_POINTS = 0, HS_K_MATCH = 1, HS_K_RAYCAST = 2, HS_K_COUNT = 3 };
@@ -185,11 +186,20 @@ int hs_create(const hs_config* cfg, hs_engine** out) {
   if (cfg->device < 0 || cfg->device >= n_dev) return HS_ERR_INVALID_ARG;
   HS_CK(cudaSetDevice(cfg->device));
 
+  // smem budgets of the two per-scan kernels grow with max_points: refuse what the device cannot launch BEFORE allocating
+  {
+    int optin = 0;
+    HS_CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device));
+    const size_t match_smem = cfg->max_points > 768 ? match2_smem_for(cfg->max_points)
+                                                    : (size_t)hs_match2_pitch(cfg->max_points) * HS_NPROD * sizeof(float) + 6 * 4 * 160 * sizeof(float) + 256;
+    if (raycast_smem_for(cfg->max_points) > (size_t)optin || match_smem > (size_t)optin) return HS_ERR_INVALID_ARG;
+  }
+  // value-initialisation: every member zero, then the default member initialisers (ray_alternate, prof_every, sm_count)
   hs_engine* e = new (std::nothrow) hs_engine();
   if (!e) return HS_ERR_OUT_OF_MEMORY;
-  memset(e, 0, sizeof(*e));
   e->prof_events = new std::vector<cudaEvent_t>();
   e->prof_ids = new std::vector<int>();
+  e->id_bitmap = new std::vector<uint64_t>();
   e->cfg = *cfg;
   e->device = cfg->device;
   HsParams& P = e->P;
@@ -418,6 +428,7 @@ int hs_destroy(hs_engine* e) {
     delete e->prof_events;
     delete e->prof_ids;
   }
+  delete e->id_bitmap;
   delete e;
   return HS_OK;
 }
@@ -609,10 +620,18 @@ static int stage_common(hs_engine* e, int n, const int32_t* ids, const int32_t* 
   return HS_OK;
 }
 
-static int check_ids(const hs_engine* e, int n, const int32_t* ids) {
+// stream ids of a batch must be in range and DISTINCT: two slots on one stream would race on its grids and counters
+static int check_ids(hs_engine* e, int n, const int32_t* ids) {
   if (!ids) return HS_OK;
-  for (int i = 0; i < n; ++i)
-    if (ids[i] < 0 || ids[i] >= e->P.n_streams) return HS_ERR_INVALID_ARG;
+  std::vector<uint64_t>& seen = *e->id_bitmap;
+  seen.assign(((size_t)e->P.n_streams + 63) / 64, 0ULL);
+  for (int i = 0; i < n; ++i) {
+    const int32_t s = ids[i];
+    if (s < 0 || s >= e->P.n_streams) return HS_ERR_INVALID_ARG;
+    const uint64_t bit = 1ULL << (s & 63);
+    if (seen[(size_t)s >> 6] & bit) return HS_ERR_INVALID_ARG;
+    seen[(size_t)s >> 6] |= bit;
+  }
   return HS_OK;
 }
 
@@ -1110,8 +1129,8 @@ int hs_match_hypotheses(hs_engine* e, int stream, const float* points, int n_poi
   return HS_OK;
 }
 
-int hs_raycast_batch(hs_engine* e, int n, const int32_t* stream_ids, const float* points, const int32_t* counts,
-                     const float* origos, const float* poses_world) {
+static int integrate_host(hs_engine* e, int n, const int32_t* stream_ids, const float* points, const int32_t* counts,
+                          const float* origos, const float* poses_world, int refresh_coarse) {
   int st = check_batch(e, n);
   if (st != HS_OK) return st;
   if (n == 0) return HS_OK;
@@ -1125,7 +1144,8 @@ int hs_raycast_batch(hs_engine* e, int n, const int32_t* stream_ids, const float
   const int32_t* d_ids = stream_ids ? e->d_ids : nullptr;
   const float2* d_or = origos ? (const float2*)e->d_origos : nullptr;
   const int threads = 128;
-  k_force_integrate<<<warp_grid(n, threads), threads, 0, e->stream>>>(e->P, n, d_ids, (const float2*)e->d_points, e->d_counts, d_or, e->d_hints);
+  k_force_integrate<<<warp_grid(n, threads), threads, 0, e->stream>>>(e->P, n, d_ids, (const float2*)e->d_points, e->d_counts, d_or, e->d_hints,
+                                                                      refresh_coarse);
   HS_LAUNCHED(e);
   {
     ProfScope ps(e, HS_K_RAYCAST);
@@ -1135,6 +1155,16 @@ int hs_raycast_batch(hs_engine* e, int n, const int32_t* stream_ids, const float
   HS_LAUNCHED(e);
   HS_CK(cudaStreamSynchronize(e->stream));
   return HS_OK;
+}
+
+int hs_raycast_batch(hs_engine* e, int n, const int32_t* stream_ids, const float* points, const int32_t* counts,
+                     const float* origos, const float* poses_world) {
+  return integrate_host(e, n, stream_ids, points, counts, origos, poses_world, 1);
+}
+
+int hs_integrate_batch(hs_engine* e, int n, const int32_t* stream_ids, const float* points, const int32_t* counts,
+                       const float* origos, const float* poses_world) {
+  return integrate_host(e, n, stream_ids, points, counts, origos, poses_world, 0);
 }
 
 // ---- off-path OccGridMapUtil members, occupancy ray queries, stream state ------------------------

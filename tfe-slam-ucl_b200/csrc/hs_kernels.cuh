@@ -958,11 +958,14 @@ __global__ void __launch_bounds__(HS_MATCH_THREADS) k_match2(HsParams P, int n_s
   }
 }
 
-// k_force_integrate: teacher-forced integration set-up (hs_raycast_batch): refresh the coarse containers from
-// the given points, take the pose from the caller and open an update epoch, as updateByScan would.
+// k_force_integrate: integration set-up with a caller-given pose (hs_raycast_batch / hs_integrate_batch): take the pose from
+// the caller and open an update epoch, as updateByScan would. refresh_coarse != 0 (teacher forcing): the coarse containers
+// are first refreshed from the given points, as matchData's setFrom would have; 0: they stay as the last matchData left
+// them -- MapRepMultiMap::updateByScan proper (MapRepMultiMap.h:134-147).
 __global__ void __launch_bounds__(128) k_force_integrate(HsParams P, int n_slots, const int32_t* __restrict__ stream_ids,
                                                          const float2* __restrict__ points, const int32_t* __restrict__ counts,
-                                                         const float2* __restrict__ origos, const float* __restrict__ poses) {
+                                                         const float2* __restrict__ origos, const float* __restrict__ poses,
+                                                         int refresh_coarse) {
   int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (slot >= n_slots) return;
@@ -971,12 +974,14 @@ __global__ void __launch_bounds__(128) k_force_integrate(HsParams P, int n_slots
   n = n < 0 ? 0 : (n > P.max_points ? P.max_points : n);
   const float2* pts = points + (size_t)slot * P.max_points;
   float2* cp = reinterpret_cast<float2*>(P.coarse_pts) + (size_t)s * P.max_points;
-  for (int i = lane; i < n; i += 32) cp[i] = pts[i];
+  if (refresh_coarse) for (int i = lane; i < n; i += 32) cp[i] = pts[i];
   if (lane == 0) {
-    P.coarse_cnt[s] = n;
-    float2 o = origos ? origos[slot] : make_float2(0.f, 0.f);
-    P.coarse_origo[2 * s] = o.x;
-    P.coarse_origo[2 * s + 1] = o.y;
+    if (refresh_coarse) {
+      P.coarse_cnt[s] = n;
+      float2 o = origos ? origos[slot] : make_float2(0.f, 0.f);
+      P.coarse_origo[2 * s] = o.x;
+      P.coarse_origo[2 * s + 1] = o.y;
+    }
     int cur = P.cur_update_index[s];
     P.slot_mark_base[slot] = cur;
     P.cur_update_index[s] = cur + 3;

@@ -1,4 +1,5 @@
-/* Deterministic synthetic LaserScan streams (host code, part of libhsgpu.so).
+/* Deterministic synthetic LaserScan streams -- the WORKLOAD GENERATOR of the tests and of bench.py (both arms), built into
+ * workload/libhsscangen.so. Not part of the product library (libhsgpu.so) and not part of the oracle.
  *
  * Produces what the callers of the hot path feed it: sensor_msgs/LaserScan range arrays shaped like
  * the RPLidar driver's output (reference: src/rplidar_ros/src/node.cpp:76-82, :331-338 -- beams at
@@ -6,12 +7,9 @@
  * drives a smooth closed loop through a rectangular room with box obstacles.
  * Everything is a pure function of (config, stream seed, scan index, beam index): no sequential RNG
  * state, so any batch of scans can be generated independently and in parallel.
- *
- * Also holds hs_scan_to_points_host, the host twin of the k_scan_to_points kernel: the arithmetic of
- * HectorMappingRos::rosLaserScanToDataContainer (src/hector_slam/hector_mapping/src/HectorMappingRos.cpp:483-507).
  */
 #define _GNU_SOURCE
-#include "hsgpu.h"
+#include "hsscangen.h"
 
 #include <math.h>
 #include <pthread.h>
@@ -122,7 +120,7 @@ static void gen_scan(const hs_scene_config* cfg, const scene_t* sc, uint64_t see
 }
 
 int hs_scene_preset(int preset, hs_scene_config* out) {
-  if (!out) return HS_ERR_INVALID_ARG;
+  if (!out) return HSG_ERR_INVALID_ARG;
   memset(out, 0, sizeof(*out));
   if (preset == HS_SCENE_RPLIDAR_ROOM) {
     out->n_beams = 360;
@@ -134,7 +132,7 @@ int hs_scene_preset(int preset, hs_scene_config* out) {
     out->n_boxes = 6; out->box_min = 0.5f; out->box_max = 1.5f;
     out->traj_rx = 2.5f; out->traj_ry = 1.8f;
     out->traj_period = 1000;
-    return HS_OK;
+    return HSG_OK;
   }
   if (preset == HS_SCENE_HIRES_HALL) {
     out->n_beams = 1440;
@@ -146,9 +144,9 @@ int hs_scene_preset(int preset, hs_scene_config* out) {
     out->n_boxes = 12; out->box_min = 1.0f; out->box_max = 4.0f;
     out->traj_rx = 8.0f; out->traj_ry = 6.0f;
     out->traj_period = 4000;
-    return HS_OK;
+    return HSG_OK;
   }
-  return HS_ERR_INVALID_ARG;
+  return HSG_ERR_INVALID_ARG;
 }
 
 typedef struct {
@@ -173,13 +171,13 @@ static void* gen_worker(void* vp) {
 
 int hs_scangen_batch(const hs_scene_config* cfg, uint64_t seed0, int n_streams, int first_scan, int n_scans,
                      float* ranges, float* truth_poses, int threads) {
-  if (!cfg || !ranges || n_streams < 0 || n_scans < 0 || cfg->n_beams <= 0 || cfg->traj_period <= 0) return HS_ERR_INVALID_ARG;
+  if (!cfg || !ranges || n_streams < 0 || n_scans < 0 || cfg->n_beams <= 0 || cfg->traj_period <= 0) return HSG_ERR_INVALID_ARG;
   if (threads < 1) threads = 1;
   if (threads > 256) threads = 256;
   if (threads > n_streams) threads = n_streams > 0 ? n_streams : 1;
   gen_arg* args = (gen_arg*)malloc(sizeof(gen_arg) * threads);
   pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * threads);
-  if (!args || !th) { free(args); free(th); return HS_ERR_OUT_OF_MEMORY; }
+  if (!args || !th) { free(args); free(th); return HSG_ERR_OUT_OF_MEMORY; }
   for (int t = 0; t < threads; ++t) {
     gen_arg a = { cfg, seed0, n_streams, first_scan, n_scans, ranges, truth_poses, threads, t };
     args[t] = a;
@@ -188,69 +186,5 @@ int hs_scangen_batch(const hs_scene_config* cfg, uint64_t seed0, int n_streams, 
   gen_worker(&args[0]);
   for (int t = 1; t < threads; ++t) pthread_join(th[t], NULL);
   free(args); free(th);
-  return HS_OK;
-}
-
-/* HectorMappingRos::rosLaserScanToDataContainer (HectorMappingRos.cpp:483-507): float angle accumulation,
- * strict (range_min, range_max - 0.1) window, dist *= scaleToMap, (cos(angle)*dist, sin(angle)*dist). */
-int hs_scan_to_points_host(const float* ranges, int n_beams, float angle_min, float angle_increment,
-                           float range_min, float range_max, float scale_to_map, float* points_out) {
-  float angle = angle_min;
-  float max_range_for_container = range_max - 0.1f;
-  int n = 0;
-  for (int i = 0; i < n_beams; ++i) {
-    float dist = ranges[i];
-    if ((dist > range_min) && (dist < max_range_for_container)) {
-      dist *= scale_to_map;
-      points_out[2 * n] = cosf(angle) * dist;
-      points_out[2 * n + 1] = sinf(angle) * dist;
-      ++n;
-    }
-    angle += angle_increment;
-  }
-  return n;
-}
-
-/* Threaded batch form of hs_scan_to_points_host: ranges [n_scans][n_beams] -> points [n_scans][max_points][2]
- * (zero padded), counts [n_scans]. */
-typedef struct {
-  const float* ranges; int n_scans, n_beams; float amin, ainc, rmin, rmax, scale; int max_points; float* pts; int32_t* cnt;
-  int threads, tid;
-} s2p_arg;
-
-static void* s2p_worker(void* vp) {
-  s2p_arg* a = (s2p_arg*)vp;
-  int k0 = (int)((long long)a->n_scans * a->tid / a->threads), k1 = (int)((long long)a->n_scans * (a->tid + 1) / a->threads);
-  float* tmp = (float*)malloc(sizeof(float) * 2 * (size_t)a->n_beams);
-  for (int k = k0; k < k1; ++k) {
-    int c = hs_scan_to_points_host(a->ranges + (size_t)k * a->n_beams, a->n_beams, a->amin, a->ainc, a->rmin, a->rmax, a->scale, tmp);
-    if (c > a->max_points) c = a->max_points;
-    float* out = a->pts + (size_t)k * a->max_points * 2;
-    memcpy(out, tmp, sizeof(float) * 2 * (size_t)c);
-    memset(out + 2 * (size_t)c, 0, sizeof(float) * 2 * (size_t)(a->max_points - c));
-    a->cnt[k] = c;
-  }
-  free(tmp);
-  return NULL;
-}
-
-int hs_scan_to_points_host_batch(const float* ranges, int n_scans, int n_beams, float angle_min, float angle_increment,
-                                 float range_min, float range_max, float scale_to_map, int max_points,
-                                 float* points_out, int32_t* counts_out, int threads) {
-  if (!ranges || !points_out || !counts_out || n_scans < 0 || n_beams < 1 || max_points < 1) return HS_ERR_INVALID_ARG;
-  if (threads < 1) threads = 1;
-  if (threads > 256) threads = 256;
-  if (threads > n_scans) threads = n_scans > 0 ? n_scans : 1;
-  s2p_arg* args = (s2p_arg*)malloc(sizeof(s2p_arg) * threads);
-  pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * threads);
-  if (!args || !th) { free(args); free(th); return HS_ERR_OUT_OF_MEMORY; }
-  for (int t = 0; t < threads; ++t) {
-    s2p_arg a = { ranges, n_scans, n_beams, angle_min, angle_increment, range_min, range_max, scale_to_map, max_points, points_out, counts_out, threads, t };
-    args[t] = a;
-    if (t > 0) pthread_create(&th[t], NULL, s2p_worker, &args[t]);
-  }
-  s2p_worker(&args[0]);
-  for (int t = 1; t < threads; ++t) pthread_join(th[t], NULL);
-  free(args); free(th);
-  return HS_OK;
+  return HSG_OK;
 }
