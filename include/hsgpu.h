@@ -176,6 +176,12 @@ const float* hs_device_pose_ptr(const hs_engine* e);
  * level: H9 [n_poses][9], dTr3 [n_poses][3]. All host pointers. */
 int hs_hessian_derivs_batch(hs_engine* e, int stream, int level, const float* poses_map, int n_poses,
                             const float* points, int n_points, float* H9, float* dTr3);
+/* The same with every pointer in DEVICE memory on the engine's GPU: asynchronous on the engine's stream, no copies and no
+ * synchronisation (a relocaliser scoring hypotheses in a loop keeps poses and results on the device). The level's
+ * log-odds are converted to probabilities once (a plane of 2x2 probability blocks, the GPU form of the reference's
+ * GridMapCacheArray) and reused by later calls until the stream's maps change. */
+int hs_hessian_derivs_batch_device(hs_engine* e, int stream, int level, const float* poses_map, int n_poses,
+                                   const float* points, int n_points, float* H9, float* dTr3);
 /* Relocalisation-style multi-start matching (BASELINE configs[3]): MapRepMultiMap::matchData (MapRepMultiMap.h:116-132) of ONE
  * scan (points [n_points][2], level-0 cells) against ONE stream's maps from n_hyp world pose hints [n_hyp][3] at once.
  * The stream's state is not touched (no pose, no coarse containers, no integration). poses_out [n_hyp][3], cov_out
@@ -270,10 +276,12 @@ typedef struct {
 int hs_get_stats(hs_engine* e, hs_stats* out);
 
 /* Per-kernel device time, measured with CUDA events recorded on the launching stream around every hot-path
- * kernel while enabled. Index: 0 k_scan_to_points, 1 k_match, 2 k_raycast. */
+ * kernel while enabled. Index: 0 k_scan_to_points, 1 k_match / k_match2, 2 k_raycast, 3 k_hessian_derivs, 4 k_build_pblk
+ * (the probability block plane behind the hypothesis entry points); the rest is reserved. */
+#define HS_PROFILE_KERNELS 8
 typedef struct {
-  double ms[3];
-  uint64_t launches[3];
+  double ms[HS_PROFILE_KERNELS];
+  uint64_t launches[HS_PROFILE_KERNELS];
 } hs_kernel_times;
 /* on: 0 = off, 1 = around every kernel, n > 1 = around the kernels of every n-th update only (the event pairs keep
  * consecutive kernels from overlapping their launch and drain, ~6 us per pair, so a sampled measurement perturbs less). */

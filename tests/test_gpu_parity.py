@@ -73,6 +73,80 @@ def test_hessian_derivs_parity(hs, oracle):
             assert np.abs((df - dc) / dscale).max() < 1e-4
 
 
+def test_hessian_derivs_4096_hypotheses_host_and_device_entry_points(hs, oracle):
+    """BASELINE configs[3] at its full size: 4096 pose hypotheses of one 360-beam scan through getCompleteHessianDerivs,
+    strict mode bit-exact against the oracle; every poses-per-warp instantiation; the device-pointer entry point; and the
+    probability block plane follows the map when it changes (update, upload, reset)."""
+    import os
+    import torch
+    n_scans, n_hyp = 30, 4096
+    sc, ranges, pts, cnt, truth = make_streams(hs, 2, n_scans + 6, seed0=31337)
+    cpus = cpu_streams(oracle, 2, dist=0.0, ang=0.0, free=0.4, occ=0.9)
+    rng = np.random.default_rng(11)
+    old = os.environ.get("HSGPU_HD_PPW")
+    try:
+        for ppw in ("0", "1", "2", "3"):
+            os.environ["HSGPU_HD_PPW"] = ppw
+            with hs.Engine(n_streams=2, max_points=360) as eng:
+                configure(eng, dist=0.0, ang=0.0, free=0.4, occ=0.9)
+                if ppw == "0":
+                    for k in range(n_scans):
+                        eng.update_batch(pts[k], cnt[k])
+                        for s, c in enumerate(cpus):
+                            c.update(pts[k, s], cnt[k, s], hint=c.pose())
+                else:
+                    for s, c in enumerate(cpus):
+                        for l in range(3):
+                            eng.upload_level(s, l, c.download_level(l))
+                for s in (1, 0):
+                    base = cpus[s].world_to_map(0, cpus[s].pose())
+                    poses = (base[None, :] + rng.uniform(-1, 1, (n_hyp, 3)).astype(np.float32) * np.array([20, 20, 0.5], np.float32)).astype(np.float32)
+                    poses[7] = (-50.0, 3000.0, 0.3)          # every point out of the map: H = 0, dTr = 0
+                    k = n_scans + s
+                    p = pts[k, s, :cnt[k, s]].copy()
+                    Hc, dc = cpus[s].hessian_derivs_batch(0, poses, p)
+                    Hg, dg = eng.hessian_derivs_batch(s, 0, poses, p)
+                    assert np.array_equal(bits(Hg), bits(Hc)) and np.array_equal(bits(dg), bits(dc)), (ppw, s)
+                    assert not Hg[7].any() and not dg[7].any()
+                    if ppw in ("0", "3"):
+                        d_pose = torch.from_numpy(poses).cuda(); d_pts = torch.from_numpy(p).cuda()
+                        d_H = torch.zeros((n_hyp, 9), device="cuda"); d_d = torch.zeros((n_hyp, 3), device="cuda")
+                        eng.hessian_derivs_batch_device(s, 0, d_pose.data_ptr(), n_hyp, d_pts.data_ptr(), p.shape[0], d_H.data_ptr(), d_d.data_ptr())
+                        eng.synchronize()
+                        assert np.array_equal(bits(d_H.cpu().numpy().reshape(n_hyp, 3, 3)), bits(Hc)) and np.array_equal(bits(d_d.cpu().numpy()), bits(dc))
+                if ppw == "0":
+                    # the plane must follow the map: another update, then an upload of a foreign map, then a reset
+                    k = n_scans + 2
+                    eng.update_batch(pts[k], cnt[k])
+                    for s, c in enumerate(cpus):
+                        c.update(pts[k, s], cnt[k, s], hint=c.pose())
+                    sub = poses[:300]
+                    Hc, dc = cpus[0].hessian_derivs_batch(0, sub, p)
+                    Hg, dg = eng.hessian_derivs_batch(0, 0, sub, p)
+                    assert np.array_equal(bits(Hg), bits(Hc)) and np.array_equal(bits(dg), bits(dc))
+                    eng.upload_level(0, 0, cpus[1].download_level(0))
+                    Hc1, dc1 = cpus[1].hessian_derivs_batch(0, sub, p)
+                    Hg, dg = eng.hessian_derivs_batch(0, 0, sub, p)
+                    assert np.array_equal(bits(Hg), bits(Hc1)) and np.array_equal(bits(dg), bits(dc1))
+                    eng.reset(0)
+                    Hg, dg = eng.hessian_derivs_batch(0, 0, sub, p)
+                    blank = oracle.CpuProcessor("port")
+                    Hb, db = blank.hessian_derivs_batch(0, sub, p)
+                    assert np.array_equal(bits(Hg), bits(Hb)) and np.array_equal(bits(dg), bits(db))
+                    # fast (tree) mode stays within tolerance at the full size
+                    eng.upload_level(0, 0, cpus[0].download_level(0))
+                    eng.set_strict_summation(False)
+                    Hf, df = eng.hessian_derivs_batch(0, 0, poses, p)
+                    Hc, dc = cpus[0].hessian_derivs_batch(0, poses, p)
+                    scale = np.abs(Hc).max(axis=(1, 2), keepdims=True) + 1e-6
+                    assert np.abs((Hf - Hc) / scale).max() < 1e-5
+    finally:
+        if old is None:
+            os.environ.pop("HSGPU_HD_PPW", None)
+        else:
+            os.environ["HSGPU_HD_PPW"] = old
+
+
 def test_raycast_teacher_forced_bitexact(hs, oracle):
     """updateByScan with oracle-given poses: every cell's marker AND log-odds bits identical."""
     n_streams, n_scans = 6, 30

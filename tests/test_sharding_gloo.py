@@ -83,3 +83,68 @@ def test_two_rank_gloo_sharded_run_matches_unsharded(tmp_path):
     _, poses, _ = pyoracle.run_streams(procs, pts, cnt, threads=2)
     assert gathered.shape == (n_total, 3)
     assert np.array_equal(gathered.view(np.int32), poses[-1].view(np.int32))
+
+
+class _FakeEngine:
+    """Stands in for hs.Engine in the hypothesis-sharding host logic (no GPU here): maps are small arrays, the 'kernel' writes
+    a deterministic function of (pose, map checksum) through the raw pointers it is given, like the C ABI does."""
+
+    def __init__(self, seed):
+        rng = np.random.default_rng(seed)
+        self.maps = [np.zeros(16 * 16 >> (2 * l), dtype=np.dtype([("logOddsVal", np.float32), ("updateIndex", np.int32)])) for l in range(3)]
+        for m in self.maps:
+            m["logOddsVal"] = rng.normal(size=m.shape).astype(np.float32)
+            m["updateIndex"] = rng.integers(0, 100, m.shape)
+
+    def level_dims(self, l):
+        return 16 >> l, 16 >> l, 0.05 * (1 << l)
+
+    def download_level(self, stream, l):
+        return self.maps[l].copy()
+
+    def upload_level(self, stream, l, cells):
+        self.maps[l] = np.array(cells, copy=True)
+
+    def hessian_derivs_batch_device(self, stream, level, poses_ptr, n, pts_ptr, n_pts, H_ptr, d_ptr):
+        import ctypes
+        poses = np.ctypeslib.as_array((ctypes.c_float * (3 * n)).from_address(poses_ptr)).reshape(n, 3)
+        H = np.ctypeslib.as_array((ctypes.c_float * (9 * n)).from_address(H_ptr)).reshape(n, 9)
+        d = np.ctypeslib.as_array((ctypes.c_float * (3 * n)).from_address(d_ptr)).reshape(n, 3)
+        key = np.float32(self.maps[level]["logOddsVal"].sum() + self.maps[level]["updateIndex"].sum())
+        H[:] = (poses.sum(axis=1, keepdims=True) * np.arange(1, 10, dtype=np.float32)[None, :] + key).astype(np.float32)
+        d[:] = (poses * np.float32(2.0) + key).astype(np.float32)
+
+
+def _hyp_worker(rank, world, port, n_hyp, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tfe_slam_ucl_b200 import hypothesis_sharding as hsd
+    eng = _FakeEngine(seed=100 + rank)              # every rank starts with DIFFERENT maps; rank 1 owns the truth
+    nbytes = hsd.replicate_stream_maps(eng, torch, dist, 1, rank, device="cpu")
+    poses = torch.from_numpy(np.random.default_rng(5).normal(size=(n_hyp, 3)).astype(np.float32))
+    pts = torch.zeros((4, 2))
+    H = torch.zeros((n_hyp, 9)); d = torch.zeros((n_hyp, 3))
+    hsd.evaluate_sharded(eng, torch, dist, rank, world, 0, poses, n_hyp, pts, 4, H, d)
+    np.save(os.path.join(out_dir, "hyp_%d.npy" % rank), np.concatenate([H.numpy(), d.numpy()], axis=1))
+    if rank == 0:
+        np.save(os.path.join(out_dir, "hyp_bytes.npy"), np.array([nbytes]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_hypothesis_sharding_replicates_and_gathers(tmp_path):
+    """SURVEY 8(e) row 2 on CPU: the owner's maps reach the other rank, every rank evaluates its own block of the hypotheses
+    and ends up with all results, equal to one rank evaluating everything against the owner's maps."""
+    world, n_hyp = 2, 64
+    port = _free_port()
+    mp.spawn(_hyp_worker, args=(world, port, n_hyp, str(tmp_path)), nprocs=world, join=True)
+    r0, r1 = np.load(tmp_path / "hyp_0.npy"), np.load(tmp_path / "hyp_1.npy")
+    assert np.array_equal(r0.view(np.int32), r1.view(np.int32))
+    owner = _FakeEngine(seed=101)
+    poses = np.random.default_rng(5).normal(size=(n_hyp, 3)).astype(np.float32)
+    H = np.zeros((n_hyp, 9), np.float32); d = np.zeros((n_hyp, 3), np.float32)
+    owner.hessian_derivs_batch_device(0, 0, poses.ctypes.data, n_hyp, 0, 4, H.ctypes.data, d.ctypes.data)
+    assert np.array_equal(r0.view(np.int32), np.concatenate([H, d], axis=1).view(np.int32))
+    assert int(np.load(tmp_path / "hyp_bytes.npy")[0]) == (256 + 64 + 16) * 8

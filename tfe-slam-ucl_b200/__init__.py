@@ -58,10 +58,10 @@ class HsStreamState(ctypes.Structure):
 
 
 class HsKernelTimes(ctypes.Structure):
-    _fields_ = [("ms", ctypes.c_double * 3), ("launches", ctypes.c_uint64 * 3)]
+    _fields_ = [("ms", ctypes.c_double * 8), ("launches", ctypes.c_uint64 * 8)]
 
 
-KERNEL_NAMES = ("k_scan_to_points", "k_match", "k_raycast")
+KERNEL_NAMES = ("k_scan_to_points", "k_match", "k_raycast", "k_hessian_derivs", "k_build_pblk")
 
 
 def build(verbose=False):
@@ -109,6 +109,7 @@ def lib():
         "hs_get_poses": (_I, [_P, _I, _I, _P]), "hs_get_covariances": (_I, [_P, _I, _I, _P]),
         "hs_get_last_map_update_poses": (_I, [_P, _I, _I, _P]), "hs_device_pose_ptr": (_P, [_P]),
         "hs_hessian_derivs_batch": (_I, [_P, _I, _I, _P, _I, _P, _I, _P, _P]),
+        "hs_hessian_derivs_batch_device": (_I, [_P, _I, _I, _P, _I, _P, _I, _P, _P]),
         "hs_match_batch": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _P]),
         "hs_match_hypotheses": (_I, [_P, _I, _P, _I, _P, _I, _P, _P]),
         "hs_raycast_batch": (_I, [_P, _I, _P, _P, _P, _P, _P]),
@@ -354,6 +355,11 @@ class Engine:
                                              points.shape[0], H.ctypes.data, d.ctypes.data), "hs_hessian_derivs_batch")
         return H.reshape(n, 3, 3), d
 
+    def hessian_derivs_batch_device(self, stream, level, poses_dptr, n_poses, points_dptr, n_points, H9_dptr, dTr3_dptr):
+        """Device pointers in and out, asynchronous on the engine's stream."""
+        _check(lib().hs_hessian_derivs_batch_device(self._h, stream, level, poses_dptr, n_poses, points_dptr, n_points, H9_dptr, dTr3_dptr),
+               "hs_hessian_derivs_batch_device")
+
     # off-path OccGridMapUtil members (OccGridMapUtil.h:106-285) and hector_map_tools ray queries
     def likelihood_batch(self, stream, level, poses_map, points):
         """(getResidualForState, getLikelihoodForState) per pose hypothesis."""
@@ -463,7 +469,7 @@ class Engine:
     def profile_collect(self):
         t = HsKernelTimes()
         _check(lib().hs_profile_collect(self._h, ctypes.byref(t)), "hs_profile_collect")
-        return {KERNEL_NAMES[i]: {"ms": t.ms[i], "launches": int(t.launches[i])} for i in range(3)}
+        return {KERNEL_NAMES[i]: {"ms": t.ms[i], "launches": int(t.launches[i])} for i in range(len(KERNEL_NAMES))}
 
     def stats(self):
         s = HsStats()

@@ -63,9 +63,14 @@ struct hs_engine {
   std::vector<int>* prof_ids;
   size_t prof_used;
   std::vector<uint64_t>* id_bitmap;        // check_ids scratch
+  // probability block plane of one (stream, level) for the hypothesis kernels (ensure_pblk)
+  float4* pblk;
+  int pblk_stream;
+  uint64_t pblk_epoch, map_epoch;          // map_epoch: bumped whenever cells of any stream may have been written
+  int hd_ppw;                              // HSGPU_HD_PPW: poses per warp in k_hessian_derivs (0 = by batch size)
 };
 
-enum { HS_K_SCAN_TO_POINTS = 0, HS_K_MATCH = 1, HS_K_RAYCAST = 2, HS_K_COUNT = 3 };
+enum { HS_K_SCAN_TO_POINTS = 0, HS_K_MATCH = 1, HS_K_RAYCAST = 2, HS_K_HESSIAN = 3, HS_K_BUILD_PBLK = 4, HS_K_COUNT = HS_PROFILE_KERNELS };
 
 struct ProfScope {
   hs_engine* e;
@@ -229,6 +234,7 @@ int hs_create(const hs_config* cfg, hs_engine** out) {
     if (const char* k = getenv("HSGPU_MATCH_L2_LEVELS")) P.l2_keep_levels = atoi(k);
     P.tail_slots = 2 * n_sm;   // measured on B200 (148 SMs): 0 -> 179 us, 148 -> 178, 296 -> 176, 444 -> 178.5, 600 -> 181
   }
+  if (const char* pw = getenv("HSGPU_HD_PPW")) e->hd_ppw = atoi(pw);
   if (const char* ts = getenv("HSGPU_RAYCAST_TAIL_SLOTS")) P.tail_slots = atoi(ts) < 0 ? 0 : atoi(ts);
   P.strict = 1;  // reference-order sums by default: bitwise the CPU reference's poses
 
@@ -406,7 +412,7 @@ int hs_destroy(hs_engine* e) {
   void* ptrs[] = {P.val, P.idx, P.last_pose, P.last_update_pose, P.cov, P.cur_update_index, P.last_update_index,
                   P.coarse_pts, P.coarse_cnt, P.coarse_origo, P.slot_pose, P.slot_sc, P.slot_integrate, P.slot_mark_base, P.counters,
                   e->d_points, e->d_counts, e->d_origos, e->d_hints, e->d_flags, e->d_ids, e->d_ranges, e->d_out,
-                  e->d_beam_cs, e->d_scratch};
+                  e->d_beam_cs, e->d_scratch, e->pblk};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (e->copy_stream) { cudaStreamSynchronize(e->copy_stream); cudaStreamDestroy(e->copy_stream); }
@@ -437,6 +443,7 @@ int hs_reset(hs_engine* e, int stream) {
   if (!e) return HS_ERR_INVALID_ARG;
   if (stream != HS_ALL_STREAMS && (stream < 0 || stream >= e->P.n_streams)) return HS_ERR_INVALID_ARG;
   HS_CK(cudaSetDevice(e->device));
+  e->map_epoch++;
   int first = stream == HS_ALL_STREAMS ? 0 : stream;
   int n = stream == HS_ALL_STREAMS ? e->P.n_streams : 1;
   k_reset_state<<<(n + 127) / 128, 128, 0, e->stream>>>(e->P, first, n, 0);
@@ -577,6 +584,7 @@ static int run_update_device(hs_engine* e, int n, const int32_t* ids, const floa
   HS_LAUNCHED(e);
   if (ev_matched) HS_CK(cudaEventRecord(ev_matched, st));
   if (mode == 0) {
+    e->map_epoch++;
     Pc.reverse_order = e->ray_alternate ? (int)(e->ray_launches++ & 1u) : 0;
     {
       ProfScope ps(e, HS_K_RAYCAST);
@@ -1054,6 +1062,63 @@ const float* hs_device_pose_ptr(const hs_engine* e) { return e ? e->P.last_pose 
 
 // ---- single-function entry points --------------------------------------------------------------
 
+// The probability block planes of one stream, all levels (see k_build_pblk): built on the engine's stream when first needed
+// and kept until the stream's maps may have changed (e->map_epoch is bumped by every entry point that writes cells).
+static int ensure_pblk(hs_engine* e, int stream) {
+  if (e->pblk && e->pblk_stream == stream && e->pblk_epoch == e->map_epoch) return HS_OK;
+  if (!e->pblk) {
+    cudaError_t err = cudaMalloc((void**)&e->pblk, (size_t)e->P.cells_per_stream * sizeof(float4));
+    if (err != cudaSuccess) { cudaGetLastError(); e->pblk = nullptr; return err == cudaErrorMemoryAllocation ? HS_ERR_OUT_OF_MEMORY : (int)err; }
+  }
+  const HsLevel& L0 = e->P.lv[0];
+  dim3 grid((L0.sx + HS_PB_TX - 1) / HS_PB_TX, (L0.sy + HS_PB_TY - 1) / HS_PB_TY, e->P.n_levels);
+  {
+    ProfScope ps(e, HS_K_BUILD_PBLK);
+    k_build_pblk<<<grid, HS_PB_TX * HS_PB_TY, 0, e->stream>>>(e->P, stream, e->pblk);
+  }
+  HS_LAUNCHED(e);
+  e->pblk_stream = stream;
+  e->pblk_epoch = e->map_epoch;
+  return HS_OK;
+}
+
+int hs_hessian_derivs_batch_device(hs_engine* e, int stream, int level, const float* poses_map, int n_poses, const float* points,
+                                   int n_points, float* H9, float* dTr3) {
+  if (!e || stream < 0 || stream >= e->P.n_streams || level < 0 || level >= e->P.n_levels || n_poses < 0 || n_points < 0)
+    return HS_ERR_INVALID_ARG;
+  if (n_poses == 0) return HS_OK;
+  if (!poses_map || (!points && n_points > 0) || !H9 || !dTr3) return HS_ERR_INVALID_ARG;
+  HS_CK(cudaSetDevice(e->device));
+  int st = ensure_pblk(e, stream);
+  if (st != HS_OK) return st;
+  // poses per warp: 3 fills 27 of the chain phase's 32 lanes; small batches take fewer so that every SM gets warps
+  int ppw = n_poses >= 3 * 8 * e->sm_count ? 3 : (n_poses >= 2 * 8 * e->sm_count ? 2 : 1);
+  if (e->hd_ppw >= 1 && e->hd_ppw <= 3) ppw = e->hd_ppw;
+  const int warps_per_cta = HS_HD_THREADS / 32;
+  const size_t smem = ((size_t)2 * ((n_points + 1) & ~1) + (size_t)warps_per_cta * ppw * HS_NPROD * HS_HD_PITCH) * sizeof(float);
+  if (smem > 200 * 1024) return HS_ERR_INVALID_ARG;
+  const int n_groups = (n_poses + ppw - 1) / ppw;
+  int grid = (n_groups + warps_per_cta - 1) / warps_per_cta;
+  const int max_grid = e->sm_count * 16;
+  if (grid > max_grid) grid = max_grid;
+  const HsLevel& L = e->P.lv[level];
+  ProfScope ps(e, HS_K_HESSIAN);
+#define HS_LAUNCH_HD(STRICT_, PPW_)                                                                                                     \
+  do {                                                                                                                                  \
+    if (smem > 48 * 1024) HS_CK(cudaFuncSetAttribute(k_hessian_derivs<STRICT_, PPW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k_hessian_derivs<STRICT_, PPW_><<<grid, HS_HD_THREADS, smem, e->stream>>>(e->pblk + L.cell_offset, L, poses_map, n_poses, (const float2*)points,    \
+                                                                             n_points, H9, dTr3);                                      \
+  } while (0)
+  if (e->P.strict) {
+    if (ppw == 3) HS_LAUNCH_HD(true, 3); else if (ppw == 2) HS_LAUNCH_HD(true, 2); else HS_LAUNCH_HD(true, 1);
+  } else {
+    if (ppw == 3) HS_LAUNCH_HD(false, 3); else if (ppw == 2) HS_LAUNCH_HD(false, 2); else HS_LAUNCH_HD(false, 1);
+  }
+#undef HS_LAUNCH_HD
+  HS_LAUNCHED(e);
+  return HS_OK;
+}
+
 int hs_hessian_derivs_batch(hs_engine* e, int stream, int level, const float* poses_map, int n_poses, const float* points,
                             int n_points, float* H9, float* dTr3) {
   if (!e || stream < 0 || stream >= e->P.n_streams || level < 0 || level >= e->P.n_levels || n_poses < 0 || n_points < 0)
@@ -1061,6 +1126,7 @@ int hs_hessian_derivs_batch(hs_engine* e, int stream, int level, const float* po
   if (n_poses == 0) return HS_OK;
   if (!poses_map || (!points && n_points > 0) || !H9 || !dTr3) return HS_ERR_INVALID_ARG;
   HS_CK(cudaSetDevice(e->device));
+  // one staging block: poses | points in, H | dTr out (the outputs are contiguous so that pinned callers get one copy each way)
   size_t b_poses = (size_t)n_poses * 3 * sizeof(float), b_pts = (size_t)(n_points > 0 ? n_points : 1) * 2 * sizeof(float);
   size_t b_h = (size_t)n_poses * 9 * sizeof(float), b_d = (size_t)n_poses * 3 * sizeof(float);
   auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
@@ -1071,19 +1137,9 @@ int hs_hessian_derivs_batch(hs_engine* e, int stream, int level, const float* po
   HS_CK(cudaMemcpyAsync(base, poses_map, b_poses, cudaMemcpyHostToDevice, e->stream));
   if (n_points > 0) HS_CK(cudaMemcpyAsync(base + o_pts, points, (size_t)n_points * 2 * sizeof(float), cudaMemcpyHostToDevice, e->stream));
   e->h2d_bytes += b_poses + (size_t)n_points * 8;
-  const size_t smem = (size_t)hs_match2_pitch(n_points > 0 ? n_points : 1) * HS_NPROD * sizeof(float);
-  if (smem > 200 * 1024) return HS_ERR_INVALID_ARG;
-  if (smem > 48 * 1024) {
-    HS_CK(cudaFuncSetAttribute(k_hessian_derivs<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    HS_CK(cudaFuncSetAttribute(k_hessian_derivs<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  }
-  if (e->P.strict)
-    k_hessian_derivs<true><<<n_poses, HS_MATCH_THREADS, smem, e->stream>>>(
-        e->P, stream, level, (const float*)base, n_poses, (const float2*)(base + o_pts), n_points, (float*)(base + o_h), (float*)(base + o_d));
-  else
-    k_hessian_derivs<false><<<n_poses, HS_MATCH_THREADS, smem, e->stream>>>(
-        e->P, stream, level, (const float*)base, n_poses, (const float2*)(base + o_pts), n_points, (float*)(base + o_h), (float*)(base + o_d));
-  HS_LAUNCHED(e);
+  st = hs_hessian_derivs_batch_device(e, stream, level, (const float*)base, n_poses, (const float*)(base + o_pts), n_points,
+                                      (float*)(base + o_h), (float*)(base + o_d));
+  if (st != HS_OK) return st;
   HS_CK(cudaMemcpyAsync(H9, base + o_h, b_h, cudaMemcpyDeviceToHost, e->stream));
   HS_CK(cudaMemcpyAsync(dTr3, base + o_d, b_d, cudaMemcpyDeviceToHost, e->stream));
   e->d2h_bytes += b_h + b_d;
@@ -1144,6 +1200,7 @@ static int integrate_host(hs_engine* e, int n, const int32_t* stream_ids, const 
   const int32_t* d_ids = stream_ids ? e->d_ids : nullptr;
   const float2* d_or = origos ? (const float2*)e->d_origos : nullptr;
   const int threads = 128;
+  e->map_epoch++;
   k_force_integrate<<<warp_grid(n, threads), threads, 0, e->stream>>>(e->P, n, d_ids, (const float2*)e->d_points, e->d_counts, d_or, e->d_hints,
                                                                       refresh_coarse);
   HS_LAUNCHED(e);
@@ -1380,6 +1437,7 @@ int hs_upload_level(hs_engine* e, int stream, int level, const hs_cell* cells_in
   size_t n = (size_t)L.sx * L.sy;
   if ((st = ensure_scratch(e, n * sizeof(hs_cell))) != HS_OK) return st;
   size_t base = (size_t)stream * (size_t)e->P.cells_per_stream + (size_t)L.cell_offset;
+  e->map_epoch++;
   HS_CK(cudaMemcpyAsync(e->d_scratch, cells_in, n * sizeof(hs_cell), cudaMemcpyHostToDevice, e->stream));
   e->h2d_bytes += n * sizeof(hs_cell);
   k_unpack_cells<<<148 * 4, 256, 0, e->stream>>>((const hs_cell*)e->d_scratch, e->P.val + base, e->P.idx + base, n);

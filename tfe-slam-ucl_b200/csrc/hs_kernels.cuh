@@ -598,6 +598,9 @@ __device__ __forceinline__ void hs_match_tail(const HsParams& P, int slot, int s
 // mode: 0 = update (match + gate), 1 = match only (no gate, no integration).
 // dynamic shared memory: 9 * pitch floats (products, sum-major) | WC: per warp PPT*128 floats + PPT*32 ints | WC: 32 x 8 B expf table.
 // WC = 1: the cache misses of a warp are processed densely (hs_points_phase_wc); 0: every thread converts its own misses.
+#ifndef HS_MATCH_LEVEL_SMEM
+#define HS_MATCH_LEVEL_SMEM 1   // A/B switch: 0 = level fields from the constant bank (round 1), 1 = from shared memory, 2 = + the plane pointer
+#endif
 #define HS_MATCH_THREADS 128   // measured on B200 at 1024 streams: 64 -> 160 us, 96 -> 122, 128 -> 109, 192/256 -> 143 per launch
 
 // 7 CTAs per SM (<= 72 registers) keeps all 1024 streams of BASELINE configs[1] resident in ONE wave on 148 SMs; at 73+
@@ -609,6 +612,8 @@ __global__ void __launch_bounds__(HS_MATCH_THREADS, (PPT > 0 && PPT <= 3) ? 7 : 
                                                             const uint8_t* __restrict__ mwm_flags, int mode) {
   extern __shared__ __align__(16) float hs_prod[];
   __shared__ float s_est[5];  // ex, ey, eth, sin(eth), cos(eth)
+  __shared__ HsLevel s_lv;    // the current level's limx, limy, pt_factor, sx, max_iter (the other fields are not copied)
+  __shared__ const float* s_val;   // ... and the first cell of its log-odds plane
   const int slot = P.slot0 + blockIdx.x;
   const int tid = threadIdx.x;
   if ((int)blockIdx.x >= n_slots) return;
@@ -674,20 +679,38 @@ __global__ void __launch_bounds__(HS_MATCH_THREADS, (PPT > 0 && PPT <= 3) ? 7 : 
         }
       }
       for (int level = P.n_levels - 1; level >= 0; --level) {
-        const HsLevel& L = P.lv[level];
-        const float* val = val_s + L.cell_offset;
+        const HsLevel& Lc = P.lv[level];   // constant bank, indexed by a run-time level: only touched here, once per level
+#if HS_MATCH_LEVEL_SMEM < 2
+        const float* val = val_s + Lc.cell_offset;
+#endif
         float ex = 0.f, ey = 0.f, eth = wth;
 #pragma unroll
         for (int j = 0; j < (PPT > 0 ? PPT : 1); ++j) cache[j].key = -1;   // a new level is a new grid
         if (serial) {
-          hs_world_to_map(L, wx, wy, ex, ey);
-          if (leader) { s_est[0] = ex; s_est[1] = ey; s_est[2] = eth; s_est[3] = hs_sinf(eth); s_est[4] = hs_cosf(eth); }
+          hs_world_to_map(Lc, wx, wy, ex, ey);
+          if (leader) {
+            s_est[0] = ex; s_est[1] = ey; s_est[2] = eth; s_est[3] = hs_sinf(eth); s_est[4] = hs_cosf(eth);
+            // what every evaluation needs of the level goes to shared memory: a register-indexed constant load (LDC
+            // c[0x0][R+imm]) in front of every use was the hottest instruction of this kernel (13.5 % of the stall samples)
+            s_lv.limx = Lc.limx; s_lv.limy = Lc.limy; s_lv.pt_factor = Lc.pt_factor; s_lv.sx = Lc.sx; s_lv.max_iter = Lc.max_iter;
+            s_val = val_s + Lc.cell_offset;
+          }
         }
         __syncthreads();
-        for (int it = 0; it <= L.max_iter; ++it) {  // 1 + maxIterations evaluations, no early exit
+#if HS_MATCH_LEVEL_SMEM >= 1
+        const HsLevel& L = s_lv;   // read with immediate-address LDS wherever the evaluation needs a field
+#else
+        const HsLevel& L = Lc;
+#endif
+#if HS_MATCH_LEVEL_SMEM >= 2
+        const float* val = s_val;
+#endif
+        const int max_iter = L.max_iter;
+        const bool keep_l2 = ((P.l2_keep_levels >> level) & 1) != 0;
+        for (int it = 0; it <= max_iter; ++it) {  // 1 + maxIterations evaluations, no early exit
           const float cex = s_est[0], cey = s_est[1], csn = s_est[3], ccs = s_est[4];
           a = hs_eval_cta<STRICT, PPT, WC>(val, L, cex, cey, csn, ccs, pts, preg, cache, n, L.pt_factor, hs_prod, hs_match2_pitch(P.max_points), sw, &mt,
-                                           w_addr, w_prob, s_tab, i0, istride, ((P.l2_keep_levels >> level) & 1) != 0);
+                                           w_addr, w_prob, s_tab, i0, istride, keep_l2);
           if (serial) {
             clamps += hs_gauss_newton_step(a, ex, ey, eth) ? 1u : 0u;
             if (leader) { s_est[0] = ex; s_est[1] = ey; s_est[2] = eth; s_est[3] = hs_sinf(eth); s_est[4] = hs_cosf(eth); }
@@ -697,7 +720,7 @@ __global__ void __launch_bounds__(HS_MATCH_THREADS, (PPT > 0 && PPT <= 3) ? 7 : 
         }
         if (serial) {
           eth = hs_normalize_angle(eth);
-          hs_map_to_world(L, ex, ey, wx, wy);
+          hs_map_to_world(Lc, ex, ey, wx, wy);
           wth = eth;
         }
       }
@@ -993,27 +1016,215 @@ __global__ void __launch_bounds__(128) k_force_integrate(HsParams P, int n_slots
   }
 }
 
-// k_hessian_derivs: getCompleteHessianDerivs for many pose hypotheses against one stream's level
-// (BASELINE config 4). One CTA per pose; pts are already scaled to the level. dynamic smem: n_pts * 9 floats.
-template <bool STRICT>
-__global__ void __launch_bounds__(HS_MATCH_THREADS) k_hessian_derivs(HsParams P, int stream, int level, const float* __restrict__ poses_map,
-                                                                     int n_poses, const float2* __restrict__ pts, int n_pts,
-                                                                     float* __restrict__ H9, float* __restrict__ dTr3) {
-  extern __shared__ __align__(16) float hs_prod[];
-  const int k = blockIdx.x;
-  if (k >= n_poses) return;
-  const HsLevel& L = P.lv[level];
-  const float* val = P.val + (size_t)stream * P.cells_per_stream + L.cell_offset;
-  const float th = poses_map[3 * k + 2];
-  HsAcc a = hs_eval_cta<STRICT, 0>(val, L, poses_map[3 * k], poses_map[3 * k + 1], hs_sinf(th), hs_cosf(th), pts, nullptr, nullptr, n_pts, 1.0f, hs_prod,
-                                   hs_match2_pitch(n_pts));
-  if (threadIdx.x == 0) {
-    float* h = H9 + 9 * (size_t)k;
-    h[0] = a.h00; h[1] = a.h01; h[2] = a.h02;
-    h[3] = a.h01; h[4] = a.h11; h[5] = a.h12;
-    h[6] = a.h02; h[7] = a.h12; h[8] = a.h22;
-    float* d = dTr3 + 3 * (size_t)k;
-    d[0] = a.d0; d[1] = a.d1; d[2] = a.d2;
+// ------------------------------------------------------------------------------------------------
+// BASELINE configs[3]: getCompleteHessianDerivs (OccGridMapUtil.h:64-104) of ONE stream's level for thousands of pose
+// hypotheses of one scan (relocalisation-style multi-start).
+//
+// Every hypothesis gathers from the same map, and log-odds -> probability (GridMapLogOddsFunctions::getGridProbability,
+// GridMapLogOdds.h:163-166: a double-precision expf and an IEEE division per cell) is a pure function of the cell. So the
+// conversion is done ONCE per cell into a "probability block plane" -- the B200 form of the reference's GridMapCacheArray
+// (HSL/map/GridMapCacheArray.h), laid out for the gather instead of per cell:
+//     pblk[k] = ( P(k), P(k+1), P(k+W), P(k+W+1) )       16 bytes: the 2x2 block interpMapValueWithDerivatives reads
+//                                                         at a point whose integer cell is k (OccGridMapUtil.h:300-335)
+// A point evaluation is then ONE 16-byte load (one 32-byte sector) and the bilinear arithmetic; 4096 hypotheses x 360 points
+// do 1.47 M block loads instead of 5.9 M cell loads + 5.9 M expf/divisions. The plane of a level (16 MB for 1024^2) stays in
+// the 126 MB L2 while the hypotheses run; the engine keeps it until the stream's maps change.
+
+// k_build_pblk: all levels of one stream in one launch (blockIdx.z = level; the plane uses the stream slab's cell offsets).
+// One 32 x 8 tile of blocks per CTA; the tile's 33 x 9 probabilities are computed once into shared memory.
+#define HS_PB_TX 32
+#define HS_PB_TY 8
+__global__ void __launch_bounds__(HS_PB_TX * HS_PB_TY) k_build_pblk(HsParams P, int stream, float4* __restrict__ pblk_stream) {
+  __shared__ float sp[HS_PB_TY + 1][HS_PB_TX + 1];
+  const HsLevel& L = P.lv[blockIdx.z];
+  const int W = L.sx, H = L.sy;
+  const int x0 = blockIdx.x * HS_PB_TX, y0 = blockIdx.y * HS_PB_TY;
+  if (x0 >= W || y0 >= H) return;
+  const float* __restrict__ val = P.val + (size_t)stream * P.cells_per_stream + L.cell_offset;
+  float4* __restrict__ pblk = pblk_stream + L.cell_offset;
+  for (int t = threadIdx.x; t < (HS_PB_TY + 1) * (HS_PB_TX + 1); t += blockDim.x) {
+    const int ty = t / (HS_PB_TX + 1), tx = t - ty * (HS_PB_TX + 1);
+    const int x = x0 + tx, y = y0 + ty;
+    float pr = 0.0f;
+    if (x < W && y < H) pr = hs_probability(__ldg(val + (size_t)y * W + x));
+    sp[ty][tx] = pr;
+  }
+  __syncthreads();
+  const int tx = threadIdx.x & (HS_PB_TX - 1), ty = threadIdx.x / HS_PB_TX;
+  const int x = x0 + tx, y = y0 + ty;
+  if (x < W && y < H) pblk[(size_t)y * W + x] = make_float4(sp[ty][tx], sp[ty][tx + 1], sp[ty + 1][tx], sp[ty + 1][tx + 1]);
+}
+
+// Per-point terms from the four probabilities of the block (the arithmetic of hs_point_terms, OccGridMapUtil.h:318-346).
+__device__ __forceinline__ void hs_block_terms(const float4 b, float fx, float fy, float sn, float cs, float px, float py, bool inside,
+                                               float& gx, float& gy, float& rot, float& fv) {
+  float m = 0.0f;
+  gx = 0.0f;
+  gy = 0.0f;
+  if (inside) {
+    const float dx1 = b.x - b.y, dx2 = b.z - b.w;
+    const float dy1 = b.x - b.z, dy2 = b.y - b.w;
+    const float x_inv = 1.0f - fx, y_inv = 1.0f - fy;
+    m = ((b.x * x_inv + b.y * fx) * y_inv) + ((b.z * x_inv + b.w * fx) * fy);
+    gx = -((dx1 * x_inv) + (dx2 * fx));  // the reference blends with the x factors here (OccGridMapUtil.h:344)
+    gy = -((dy1 * y_inv) + (dy2 * fy));  // ... and with the y factors here (:345)
+  }
+  fv = 1.0f - m;
+  rot = ((-sn * px - cs * py) * gx + (cs * px - sn * py) * gy);
+}
+
+// k_hessian_derivs: every WARP works on its own group of PPW hypotheses, no CTA barrier after the points are staged.
+//   point phase  the 32 lanes evaluate a chunk of HS_HD_CHUNK points for each of the PPW poses (all block loads of the chunk
+//                are issued before the first is used) and leave the nine products per point in the warp's shared-memory
+//                buffer, sum-major: w[(j*9 + k) * pitch + e]
+//   chain phase  STRICT: lane j*9 + k (27 of 32 lanes busy for PPW = 3) extends sum k of pose j by the chunk's products in
+//                the reference's point order (OccGridMapUtil.h:76-98), four terms per 16-byte shared load -- the dependent
+//                FADD chain of one pose costs a warp instruction per term, so carrying three poses per warp divides the
+//                serial part's issue slots by three
+//                tree mode: no shared memory, every lane keeps 9 partial sums per pose over its points, xor-butterfly at the end
+// poses are MAP coordinates of the level, pts already scaled to it. dynamic smem: n_pts float2 (padded to 16 B) | per warp
+// PPW * 9 * (HS_HD_CHUNK + 4) floats.
+#define HS_HD_CHUNK 64
+#define HS_HD_PITCH (HS_HD_CHUNK + 4)   // == 4 (mod 32): conflict-free 16-byte reads by lanes that own different sums
+#define HS_HD_THREADS 128
+
+template <bool STRICT, int PPW>
+__global__ void __launch_bounds__(HS_HD_THREADS) k_hessian_derivs(const float4* __restrict__ pblk, HsLevel L, const float* __restrict__ poses_map,
+                                                                  int n_poses, const float2* __restrict__ pts, int n_pts,
+                                                                  float* __restrict__ H9, float* __restrict__ dTr3) {
+  extern __shared__ __align__(16) float hs_hd[];
+  float2* spts = reinterpret_cast<float2*>(hs_hd);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* w = hs_hd + 2 * ((n_pts + 1) & ~1) + warp * (PPW * HS_NPROD * HS_HD_PITCH);
+  for (int i = threadIdx.x; i < n_pts; i += blockDim.x) spts[i] = pts[i];
+  __syncthreads();
+  const int W = L.sx;
+  const float limx = L.limx, limy = L.limy;
+  const int n_groups = (n_poses + PPW - 1) / PPW;
+  constexpr int R = HS_HD_CHUNK / 32;
+  for (int g = blockIdx.x * (HS_HD_THREADS / 32) + warp; g < n_groups; g += gridDim.x * (HS_HD_THREADS / 32)) {
+    // lane j < PPW loads pose j of the group and computes its sin/cos once; everybody else gets them by shuffle
+    float mx = 0.0f, my = 0.0f, msn = 0.0f, mcs = 1.0f;
+    if (lane < PPW && g * PPW + lane < n_poses) {
+      const float* pm = poses_map + 3 * (size_t)(g * PPW + lane);
+      mx = pm[0]; my = pm[1];
+      const float th = pm[2];
+      msn = hs_sinf(th); mcs = hs_cosf(th);
+    }
+    float ex[PPW], ey[PPW], sn[PPW], cs[PPW];
+#pragma unroll
+    for (int j = 0; j < PPW; ++j) {
+      ex[j] = __shfl_sync(0xffffffffu, mx, j); ey[j] = __shfl_sync(0xffffffffu, my, j);
+      sn[j] = __shfl_sync(0xffffffffu, msn, j); cs[j] = __shfl_sync(0xffffffffu, mcs, j);
+    }
+    float acc = 0.0f;                    // STRICT: sum (lane % 9) of pose (lane / 9)
+    float part[STRICT ? 1 : PPW][HS_NPROD];   // tree mode: this lane's partial sums
+    if (!STRICT) {
+#pragma unroll
+      for (int j = 0; j < PPW; ++j)
+#pragma unroll
+        for (int k = 0; k < HS_NPROD; ++k) part[j][k] = 0.0f;
+    }
+    for (int c0 = 0; c0 < n_pts; c0 += HS_HD_CHUNK) {
+      const int len = min(HS_HD_CHUNK, n_pts - c0);
+      // point phase, step 1: block addresses, all loads in flight
+      float4 blk[PPW][R];
+      float fxs[PPW][R], fys[PPW][R];
+      unsigned inside = 0u;
+#pragma unroll
+      for (int j = 0; j < PPW; ++j) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int i = c0 + r * 32 + lane;
+          blk[j][r] = make_float4(0.f, 0.f, 0.f, 0.f);
+          fxs[j][r] = 0.0f; fys[j][r] = 0.0f;
+          if (i < n_pts) {
+            const float2 p = spts[i];
+            const float qx = (cs[j] * p.x + (-sn[j]) * p.y) + ex[j];  // Affine2f * v = linear*v + translation
+            const float qy = (sn[j] * p.x + cs[j] * p.y) + ey[j];
+            if (qx >= 0.0f && qx <= limx && qy >= 0.0f && qy <= limy) {  // !pointOutOfMapBounds
+              const int ix = (int)qx, iy = (int)qy;
+              fxs[j][r] = qx - (float)ix; fys[j][r] = qy - (float)iy;
+              blk[j][r] = __ldg(pblk + (size_t)iy * W + ix);
+              inside |= 1u << (j * R + r);
+            }
+          }
+        }
+      }
+      // step 2: terms and products
+#pragma unroll
+      for (int j = 0; j < PPW; ++j) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int e = r * 32 + lane;
+          if (c0 + e < n_pts) {
+            const float2 p = spts[c0 + e];
+            float gx, gy, rot, fv;
+            hs_block_terms(blk[j][r], fxs[j][r], fys[j][r], sn[j], cs[j], p.x, p.y, (inside >> (j * R + r)) & 1u, gx, gy, rot, fv);
+            if (STRICT) {
+              hs_store_products(w + j * HS_NPROD * HS_HD_PITCH + e, HS_HD_PITCH, gx, gy, rot, fv);
+            } else {
+              float* a = part[STRICT ? 0 : j];
+              a[0] += gx * fv; a[1] += gy * fv; a[2] += rot * fv; a[3] += gx * gx; a[4] += gy * gy; a[5] += rot * rot;
+              a[6] += gx * gy; a[7] += gx * rot; a[8] += gy * rot;
+            }
+          }
+        }
+      }
+      if (STRICT) {
+        __syncwarp();
+        if (lane < PPW * HS_NPROD) {
+          const float* q = w + lane * HS_HD_PITCH;
+          const float4* q4 = reinterpret_cast<const float4*>(q);
+          const int n4 = len >> 2;
+          for (int e = 0; e < n4; ++e) {   // loads are independent of the chain and issue ahead of it
+            const float4 t = q4[e];
+            acc += t.x; acc += t.y; acc += t.z; acc += t.w;
+          }
+          for (int e = n4 << 2; e < len; ++e) acc += q[e];
+        }
+        __syncwarp();
+      }
+    }
+    // results: sum order d0 d1 d2 h00 h11 h22 h01 h02 h12 (HsAcc)
+    if (STRICT) {
+      const int j = lane / HS_NPROD, k = lane - j * HS_NPROD;
+      const int p = g * PPW + j;
+      if (lane < PPW * HS_NPROD && p < n_poses) {
+        float* h = H9 + 9 * (size_t)p;
+        float* d = dTr3 + 3 * (size_t)p;
+        switch (k) {
+          case 0: d[0] = acc; break;
+          case 1: d[1] = acc; break;
+          case 2: d[2] = acc; break;
+          case 3: h[0] = acc; break;
+          case 4: h[4] = acc; break;
+          case 5: h[8] = acc; break;
+          case 6: h[1] = acc; h[3] = acc; break;
+          case 7: h[2] = acc; h[6] = acc; break;
+          default: h[5] = acc; h[7] = acc; break;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < PPW; ++j) {
+        float* a = part[STRICT ? 0 : j];
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+#pragma unroll
+          for (int k = 0; k < HS_NPROD; ++k) a[k] += __shfl_xor_sync(0xffffffffu, a[k], m);
+        }
+        const int p = g * PPW + j;
+        if (lane == 0 && p < n_poses) {
+          float* h = H9 + 9 * (size_t)p;
+          float* d = dTr3 + 3 * (size_t)p;
+          d[0] = a[0]; d[1] = a[1]; d[2] = a[2];
+          h[0] = a[3]; h[1] = a[6]; h[2] = a[7];
+          h[3] = a[6]; h[4] = a[4]; h[5] = a[8];
+          h[6] = a[7]; h[7] = a[8]; h[8] = a[5];
+        }
+      }
+    }
   }
 }
 
