@@ -261,6 +261,19 @@ typedef struct {
 int hs_export_stream_state(hs_engine* e, int stream, hs_stream_state* out, float* coarse_points_out);
 int hs_import_stream_state(hs_engine* e, int stream, const hs_stream_state* in, const float* coarse_points);
 
+/* ---- multi-GPU plumbing for single-process callers (include/hsgpu/ShardedEngine.h) ------ */
+
+/* Number of usable CUDA devices (0 without a GPU: there is no CPU fallback). */
+int hs_device_count(void);
+/* Counter that changes whenever cells of any stream of the engine may have been written (update, integrate, upload, reset,
+ * hs_copy_stream_maps): lets a caller cache replicas of a stream's maps. */
+uint64_t hs_get_map_epoch(const hs_engine* e);
+/* Replicates all levels of src's stream src_stream into dst's stream dst_stream (same map geometry; engines on the same GPU
+ * or on peers: cudaMemcpyPeerAsync). What SURVEY 8(e) row 2 needs to shard the pose hypotheses of ONE stream over several
+ * GPUs: the owner's maps are copied into a guest stream of every other engine. Per-stream state other than cells (poses,
+ * update counters, coarse containers) is not copied. Returns when the copy has completed. */
+int hs_copy_stream_maps(hs_engine* dst, int dst_stream, hs_engine* src, int src_stream);
+
 /* ---- bookkeeping -------------------------------------------------------------------------- */
 
 typedef struct {

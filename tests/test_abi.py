@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def declared_functions():
     text = open(os.path.join(ROOT, "include", "hsgpu.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    names = re.findall(r"^\s*(?:const\s+)?(?:int|float|char\*|const char\*|const float\*)\s*\*?\s*(hs_[a-z0-9_]+)\s*\(", text, flags=re.M)
+    names = re.findall(r"^\s*(?:const\s+)?(?:int|float|uint64_t|char\*|const char\*|const float\*)\s*\*?\s*(hs_[a-z0-9_]+)\s*\(", text, flags=re.M)
     return sorted(set(names))
 
 

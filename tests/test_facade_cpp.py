@@ -209,3 +209,51 @@ def test_maprep_gpu_map_without_matching_integrates_stale_containers(tmp_path, h
         ref = p.download_level(l)
         assert ui == p.update_index(l)
         assert np.array_equal(cells["updateIndex"], ref["updateIndex"]) and np.array_equal(bits(cells["logOddsVal"]), bits(ref["logOddsVal"])), l
+
+
+def build_sharded_test(tmp_path, hs):
+    exe = str(tmp_path / "sharded_test")
+    libdir = os.path.dirname(hs.LIB_PATH)
+    cmd = ["g++", "-std=c++14", "-O2", "-I", os.path.join(ROOT, "include"), "-o", exe, os.path.join(ROOT, "tests", "cpp", "sharded_test.cpp"),
+           "-L", libdir, "-lhsgpu", "-Wl,-rpath," + libdir, "-pthread"]
+    subprocess.run(cmd, check=True)
+    return exe
+
+
+def test_sharded_engine_compiles_and_fails_loudly_without_gpu(tmp_path, hs):
+    """include/hsgpu/ShardedEngine.h (C++ multi-GPU host layer: one engine + one host thread per shard) needs nothing but the
+    C ABI and the C++ standard library."""
+    exe = build_sharded_test(tmp_path, hs)
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by test_sharded_engine_equals_one_engine")
+    inp = tmp_path / "in.bin"
+    inp.write_bytes(np.array([2, 0, 4], np.int32).tobytes())
+    res = subprocess.run([exe, str(inp), str(tmp_path / "out.bin")], capture_output=True, text=True)
+    assert res.returncode == 1 and "no usable CUDA device" in res.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_shards", [0, 3])
+def test_sharded_engine_equals_one_engine(tmp_path, hs, oracle, n_shards):
+    """Streams sharded over engines (one per visible GPU, or 3 shards round-robin over the visible GPUs) give the poses, maps and
+    hypothesis results of ONE engine holding all streams, bit for bit; the poses also equal the CPU oracle's."""
+    exe = build_sharded_test(tmp_path, hs)
+    n, n_scans, mp = 7, 8, 360
+    sc, ranges, pts, cnt, truth = make_streams(hs, n, n_scans, seed0=6060)
+    with open(tmp_path / "in.bin", "wb") as f:
+        f.write(np.array([n, n_scans, mp], np.int32).tobytes())
+        for k in range(n_scans):
+            f.write(cnt[k].astype(np.int32).tobytes())
+            f.write(pts[k].astype(np.float32).tobytes())
+    res = subprocess.run([exe, str(tmp_path / "in.bin"), str(tmp_path / "out.bin"), str(n_shards)], capture_output=True, text=True)
+    assert res.returncode == 0, (res.returncode, res.stderr)
+    assert "sharded ok" in res.stderr
+    poses = np.frombuffer(open(tmp_path / "out.bin", "rb").read(), np.float32).reshape(n_scans, n, 3)
+    procs = [oracle.CpuProcessor("port") for _ in range(n)]
+    for p in procs:
+        p.set_update_factor_free(0.4); p.set_update_factor_occupied(0.9)
+        p.set_map_update_min_dist_diff(0.0); p.set_map_update_min_angle_diff(0.0)
+    for k in range(n_scans):
+        for s, p in enumerate(procs):
+            assert np.array_equal(bits(poses[k, s]), bits(p.update(pts[k, s], cnt[k, s], hint=p.pose()))), (k, s)

@@ -124,6 +124,7 @@ def lib():
         "hs_interp_map_value_batch": (_I, [_P, _I, _I, _P, _I, _P, _P]),
         "hs_occupancy_ray_batch": (_I, [_P, _I, _I, _P, _P, _I, _P, _P]),
         "hs_export_stream_state": (_I, [_P, _I, _P, _P]), "hs_import_stream_state": (_I, [_P, _I, _P, _P]),
+        "hs_device_count": (_I, []), "hs_get_map_epoch": (ctypes.c_uint64, [_P]), "hs_copy_stream_maps": (_I, [_P, _I, _P, _I]),
         "hs_profile_enable": (_I, [_P, _I]), "hs_profile_collect": (_I, [_P, _P]),
     }
     for name, (res, args) in sig.items():
@@ -462,6 +463,13 @@ class Engine:
         out = np.empty(sx * sy, np.int8)
         _check(lib().hs_classify_level(self._h, stream, level, out.ctypes.data), "hs_classify_level")
         return out
+
+    def map_epoch(self):
+        return int(lib().hs_get_map_epoch(self._h))
+
+    def copy_stream_maps_from(self, dst_stream, src_engine, src_stream):
+        """All levels of src_engine's stream src_stream into this engine's dst_stream (same or peer GPU)."""
+        _check(lib().hs_copy_stream_maps(self._h, dst_stream, src_engine._h, src_stream), "hs_copy_stream_maps")
 
     def profile_enable(self, on=True):
         _check(lib().hs_profile_enable(self._h, int(on)), "hs_profile_enable")

@@ -68,6 +68,8 @@ struct hs_engine {
   int pblk_stream;
   uint64_t pblk_epoch, map_epoch;          // map_epoch: bumped whenever cells of any stream may have been written
   int hd_ppw;                              // HSGPU_HD_PPW: poses per warp in k_hessian_derivs (0 = by batch size)
+  void* h_pinned;                          // engine-owned pinned host staging (ensure_pinned)
+  size_t pinned_bytes;
 };
 
 enum { HS_K_SCAN_TO_POINTS = 0, HS_K_MATCH = 1, HS_K_RAYCAST = 2, HS_K_HESSIAN = 3, HS_K_BUILD_PBLK = 4, HS_K_COUNT = HS_PROFILE_KERNELS };
@@ -435,6 +437,7 @@ int hs_destroy(hs_engine* e) {
     delete e->prof_ids;
   }
   delete e->id_bitmap;
+  if (e->h_pinned) cudaFreeHost(e->h_pinned);
   delete e;
   return HS_OK;
 }
@@ -1091,8 +1094,10 @@ int hs_hessian_derivs_batch_device(hs_engine* e, int stream, int level, const fl
   HS_CK(cudaSetDevice(e->device));
   int st = ensure_pblk(e, stream);
   if (st != HS_OK) return st;
-  // poses per warp: 3 fills 27 of the chain phase's 32 lanes; small batches take fewer so that every SM gets warps
-  int ppw = n_poses >= 3 * 8 * e->sm_count ? 3 : (n_poses >= 2 * 8 * e->sm_count ? 2 : 1);
+  // poses per warp: 3 fills 27 of the chain phase's 32 lanes and divides the serial part's issue slots by three, but the
+  // kernel is latency-bound until every SM holds its 64 warps: measured on B200 at 4096 hypotheses x 360 points (strict /
+  // tree, us per launch): 1 pose per warp 19.0 / 14.3, 2: 20.8 / 16.8, 3: 23.1 / 18.9
+  int ppw = n_poses >= 3 * 64 * e->sm_count ? 3 : (n_poses >= 2 * 64 * e->sm_count ? 2 : 1);
   if (e->hd_ppw >= 1 && e->hd_ppw <= 3) ppw = e->hd_ppw;
   const int warps_per_cta = HS_HD_THREADS / 32;
   const size_t smem = ((size_t)2 * ((n_points + 1) & ~1) + (size_t)warps_per_cta * ppw * HS_NPROD * HS_HD_PITCH) * sizeof(float);
@@ -1119,6 +1124,16 @@ int hs_hessian_derivs_batch_device(hs_engine* e, int stream, int level, const fl
   return HS_OK;
 }
 
+static int ensure_pinned(hs_engine* e, size_t bytes) {
+  if (bytes <= e->pinned_bytes) return HS_OK;
+  if (e->h_pinned) cudaFreeHost(e->h_pinned);
+  e->h_pinned = nullptr;
+  e->pinned_bytes = 0;
+  HS_CK(cudaHostAlloc(&e->h_pinned, bytes, cudaHostAllocDefault));
+  e->pinned_bytes = bytes;
+  return HS_OK;
+}
+
 int hs_hessian_derivs_batch(hs_engine* e, int stream, int level, const float* poses_map, int n_poses, const float* points,
                             int n_points, float* H9, float* dTr3) {
   if (!e || stream < 0 || stream >= e->P.n_streams || level < 0 || level >= e->P.n_levels || n_poses < 0 || n_points < 0)
@@ -1126,24 +1141,30 @@ int hs_hessian_derivs_batch(hs_engine* e, int stream, int level, const float* po
   if (n_poses == 0) return HS_OK;
   if (!poses_map || (!points && n_points > 0) || !H9 || !dTr3) return HS_ERR_INVALID_ARG;
   HS_CK(cudaSetDevice(e->device));
-  // one staging block: poses | points in, H | dTr out (the outputs are contiguous so that pinned callers get one copy each way)
+  // One staging block each way, mirrored in an engine-owned PINNED host buffer: poses | points in, H | dTr out. The caller's
+  // (usually pageable) arrays are memcpy'd to / from it, so the call costs two DMA transfers instead of four driver-staged
+  // copies (measured on B200, 4096 hypotheses x 360 points: 95 -> see DESIGN.md us per call).
   size_t b_poses = (size_t)n_poses * 3 * sizeof(float), b_pts = (size_t)(n_points > 0 ? n_points : 1) * 2 * sizeof(float);
   size_t b_h = (size_t)n_poses * 9 * sizeof(float), b_d = (size_t)n_poses * 3 * sizeof(float);
   auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
   size_t o_pts = align(b_poses), o_h = o_pts + align(b_pts), o_d = o_h + align(b_h), total = o_d + align(b_d);
   int st = ensure_scratch(e, total);
   if (st != HS_OK) return st;
+  if ((st = ensure_pinned(e, total)) != HS_OK) return st;
   char* base = (char*)e->d_scratch;
-  HS_CK(cudaMemcpyAsync(base, poses_map, b_poses, cudaMemcpyHostToDevice, e->stream));
-  if (n_points > 0) HS_CK(cudaMemcpyAsync(base + o_pts, points, (size_t)n_points * 2 * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  char* hbase = (char*)e->h_pinned;
+  memcpy(hbase, poses_map, b_poses);
+  if (n_points > 0) memcpy(hbase + o_pts, points, (size_t)n_points * 2 * sizeof(float));
+  HS_CK(cudaMemcpyAsync(base, hbase, o_pts + (size_t)n_points * 2 * sizeof(float), cudaMemcpyHostToDevice, e->stream));
   e->h2d_bytes += b_poses + (size_t)n_points * 8;
   st = hs_hessian_derivs_batch_device(e, stream, level, (const float*)base, n_poses, (const float*)(base + o_pts), n_points,
                                       (float*)(base + o_h), (float*)(base + o_d));
   if (st != HS_OK) return st;
-  HS_CK(cudaMemcpyAsync(H9, base + o_h, b_h, cudaMemcpyDeviceToHost, e->stream));
-  HS_CK(cudaMemcpyAsync(dTr3, base + o_d, b_d, cudaMemcpyDeviceToHost, e->stream));
+  HS_CK(cudaMemcpyAsync(hbase + o_h, base + o_h, (o_d - o_h) + b_d, cudaMemcpyDeviceToHost, e->stream));
   e->d2h_bytes += b_h + b_d;
   HS_CK(cudaStreamSynchronize(e->stream));
+  memcpy(H9, hbase + o_h, b_h);
+  memcpy(dTr3, hbase + o_d, b_d);
   return HS_OK;
 }
 
@@ -1487,6 +1508,38 @@ int hs_get_map_info(const hs_engine* e, int level, hs_map_info* out) {
   out->resolution = res;
   out->width = L.sx;
   out->height = L.sy;
+  return HS_OK;
+}
+
+// ---- multi-GPU plumbing for single-process callers (include/hsgpu/ShardedEngine.h) ---------------------------------
+
+int hs_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+uint64_t hs_get_map_epoch(const hs_engine* e) { return e ? e->map_epoch : 0; }
+
+// Replicates all levels of one stream's maps (both planes) from one engine into a stream of another engine with the same map
+// geometry -- on the same GPU or on a peer (cudaMemcpyPeerAsync over NVLink) -- ordered after everything queued on the source
+// engine and before everything queued later on the destination engine. Returns when the copy has completed.
+int hs_copy_stream_maps(hs_engine* dst, int dst_stream, hs_engine* src, int src_stream) {
+  if (!dst || !src || dst_stream < 0 || dst_stream >= dst->P.n_streams || src_stream < 0 || src_stream >= src->P.n_streams) return HS_ERR_INVALID_ARG;
+  if (dst->P.n_levels != src->P.n_levels || dst->P.cells_per_stream != src->P.cells_per_stream || dst->P.lv[0].sx != src->P.lv[0].sx ||
+      dst->P.lv[0].sy != src->P.lv[0].sy)
+    return HS_ERR_INVALID_ARG;
+  if (dst == src && dst_stream == src_stream) return HS_OK;
+  const size_t cells = (size_t)src->P.cells_per_stream;
+  HS_CK(cudaSetDevice(src->device));
+  HS_CK(cudaStreamSynchronize(src->stream));       // the source maps are final
+  HS_CK(cudaSetDevice(dst->device));
+  dst->map_epoch++;
+  HS_CK(cudaMemcpyPeerAsync(dst->P.val + (size_t)dst_stream * cells, dst->device, src->P.val + (size_t)src_stream * cells, src->device,
+                            cells * sizeof(float), dst->stream));
+  HS_CK(cudaMemcpyPeerAsync(dst->P.idx + (size_t)dst_stream * cells, dst->device, src->P.idx + (size_t)src_stream * cells, src->device,
+                            cells * sizeof(int), dst->stream));
+  HS_CK(cudaStreamSynchronize(dst->stream));
   return HS_OK;
 }
 

@@ -598,9 +598,6 @@ __device__ __forceinline__ void hs_match_tail(const HsParams& P, int slot, int s
 // mode: 0 = update (match + gate), 1 = match only (no gate, no integration).
 // dynamic shared memory: 9 * pitch floats (products, sum-major) | WC: per warp PPT*128 floats + PPT*32 ints | WC: 32 x 8 B expf table.
 // WC = 1: the cache misses of a warp are processed densely (hs_points_phase_wc); 0: every thread converts its own misses.
-#ifndef HS_MATCH_LEVEL_SMEM
-#define HS_MATCH_LEVEL_SMEM 1   // A/B switch: 0 = level fields from the constant bank (round 1), 1 = from shared memory, 2 = + the plane pointer
-#endif
 #define HS_MATCH_THREADS 128   // measured on B200 at 1024 streams: 64 -> 160 us, 96 -> 122, 128 -> 109, 192/256 -> 143 per launch
 
 // 7 CTAs per SM (<= 72 registers) keeps all 1024 streams of BASELINE configs[1] resident in ONE wave on 148 SMs; at 73+
@@ -680,9 +677,6 @@ __global__ void __launch_bounds__(HS_MATCH_THREADS, (PPT > 0 && PPT <= 3) ? 7 : 
       }
       for (int level = P.n_levels - 1; level >= 0; --level) {
         const HsLevel& Lc = P.lv[level];   // constant bank, indexed by a run-time level: only touched here, once per level
-#if HS_MATCH_LEVEL_SMEM < 2
-        const float* val = val_s + Lc.cell_offset;
-#endif
         float ex = 0.f, ey = 0.f, eth = wth;
 #pragma unroll
         for (int j = 0; j < (PPT > 0 ? PPT : 1); ++j) cache[j].key = -1;   // a new level is a new grid
@@ -690,21 +684,17 @@ __global__ void __launch_bounds__(HS_MATCH_THREADS, (PPT > 0 && PPT <= 3) ? 7 : 
           hs_world_to_map(Lc, wx, wy, ex, ey);
           if (leader) {
             s_est[0] = ex; s_est[1] = ey; s_est[2] = eth; s_est[3] = hs_sinf(eth); s_est[4] = hs_cosf(eth);
-            // what every evaluation needs of the level goes to shared memory: a register-indexed constant load (LDC
-            // c[0x0][R+imm]) in front of every use was the hottest instruction of this kernel (13.5 % of the stall samples)
+            // what every evaluation needs of the level goes to shared memory: with `P.lv[level]` read in place, register-indexed
+            // constant loads (LDC c[0x0][R+imm]) sat in front of every use -- the loop bound's was the hottest instruction of
+            // the kernel (13.5 % of the stall samples) -- and the plane pointer was re-derived inside the miss loop. Same-box
+            // A/B on B200, 1024 streams: 99.1 us (constant bank) -> 96.0 (level fields here) -> 95.6 (+ the plane pointer)
             s_lv.limx = Lc.limx; s_lv.limy = Lc.limy; s_lv.pt_factor = Lc.pt_factor; s_lv.sx = Lc.sx; s_lv.max_iter = Lc.max_iter;
             s_val = val_s + Lc.cell_offset;
           }
         }
         __syncthreads();
-#if HS_MATCH_LEVEL_SMEM >= 1
         const HsLevel& L = s_lv;   // read with immediate-address LDS wherever the evaluation needs a field
-#else
-        const HsLevel& L = Lc;
-#endif
-#if HS_MATCH_LEVEL_SMEM >= 2
         const float* val = s_val;
-#endif
         const int max_iter = L.max_iter;
         const bool keep_l2 = ((P.l2_keep_levels >> level) & 1) != 0;
         for (int it = 0; it <= max_iter; ++it) {  // 1 + maxIterations evaluations, no early exit
@@ -884,6 +874,8 @@ __global__ void __launch_bounds__(HS_MATCH_THREADS) k_match2(HsParams P, int n_s
                                                              const uint8_t* __restrict__ mwm_flags, int mode) {
   extern __shared__ __align__(16) float hs_m2[];
   __shared__ float s_est[5];  // ex, ey, eth, sin(eth), cos(eth)
+  __shared__ HsLevel s_lv;    // the current level's limx, limy, pt_factor, sx, max_iter
+  __shared__ const float* s_val;
   __shared__ int s_nmiss;
   const int pitch = hs_match2_pitch(P.max_points);
   float* prodT = hs_m2;
@@ -940,16 +932,22 @@ __global__ void __launch_bounds__(HS_MATCH_THREADS) k_match2(HsParams P, int n_s
       HsMatchTimer mt;
       mt.begin(P.dbg_times);
       for (int level = P.n_levels - 1; level >= 0; --level) {
-        const HsLevel& L = P.lv[level];
-        const float* val = val_s + L.cell_offset;
+        const HsLevel& Lc = P.lv[level];   // constant bank, indexed by a run-time level: only touched here, once per level
         float ex = 0.f, ey = 0.f, eth = wth;
         for (int i = tid; i < n; i += blockDim.x) kcell[i] = -1;   // a new level is a new grid
         if (serial) {
-          hs_world_to_map(L, wx, wy, ex, ey);
-          if (leader) { s_est[0] = ex; s_est[1] = ey; s_est[2] = eth; s_est[3] = hs_sinf(eth); s_est[4] = hs_cosf(eth); }
+          hs_world_to_map(Lc, wx, wy, ex, ey);
+          if (leader) {
+            s_est[0] = ex; s_est[1] = ey; s_est[2] = eth; s_est[3] = hs_sinf(eth); s_est[4] = hs_cosf(eth);
+            s_lv.limx = Lc.limx; s_lv.limy = Lc.limy; s_lv.pt_factor = Lc.pt_factor; s_lv.sx = Lc.sx; s_lv.max_iter = Lc.max_iter;   // see k_match
+            s_val = val_s + Lc.cell_offset;
+          }
         }
         __syncthreads();
-        for (int it = 0; it <= L.max_iter; ++it) {  // 1 + maxIterations evaluations, no early exit
+        const HsLevel& L = s_lv;
+        const float* val = s_val;
+        const int max_iter = s_lv.max_iter;
+        for (int it = 0; it <= max_iter; ++it) {  // 1 + maxIterations evaluations, no early exit
           const float cex = s_est[0], cey = s_est[1], csn = s_est[3], ccs = s_est[4];
           a = hs_eval_cta2<STRICT>(val, L, cex, cey, csn, ccs, spts, n, L.pt_factor, prodT, pitch, pcache, kcell, miss, &s_nmiss, sw, mt);
           if (serial) {
@@ -961,7 +959,7 @@ __global__ void __launch_bounds__(HS_MATCH_THREADS) k_match2(HsParams P, int n_s
         }
         if (serial) {
           eth = hs_normalize_angle(eth);
-          hs_map_to_world(L, ex, ey, wx, wy);
+          hs_map_to_world(Lc, ex, ey, wx, wy);
           wth = eth;
         }
       }
@@ -1084,7 +1082,9 @@ __device__ __forceinline__ void hs_block_terms(const float4 b, float fx, float f
 //                tree mode: no shared memory, every lane keeps 9 partial sums per pose over its points, xor-butterfly at the end
 // poses are MAP coordinates of the level, pts already scaled to it. dynamic smem: n_pts float2 (padded to 16 B) | per warp
 // PPW * 9 * (HS_HD_CHUNK + 4) floats.
+#ifndef HS_HD_CHUNK
 #define HS_HD_CHUNK 64
+#endif
 #define HS_HD_PITCH (HS_HD_CHUNK + 4)   // == 4 (mod 32): conflict-free 16-byte reads by lanes that own different sums
 #define HS_HD_THREADS 128
 
