@@ -68,6 +68,9 @@ struct hs_engine {
   int pblk_stream;
   uint64_t pblk_epoch, map_epoch;          // map_epoch: bumped whenever cells of any stream may have been written
   int hd_ppw;                              // HSGPU_HD_PPW: poses per warp in k_hessian_derivs (0 = by batch size)
+  int match_ct_pitch;                      // HSGPU_MATCH_CT_PITCH (A/B): use the compile-time-pitch instantiation of k_match when it applies
+  int match2_threads;                      // HSGPU_MATCH2_THREADS: 128 / 256 / 512 threads per k_match2 CTA (0 = by batch size)
+  int ray_big;                             // k_raycast as one 1024-thread CTA per SM with a 144 KB map (long scans, launch_raycast)
   void* h_pinned;                          // engine-owned pinned host staging (ensure_pinned)
   size_t pinned_bytes;
 };
@@ -118,14 +121,39 @@ static int raycast_log2_hash(int max_points) {
   while ((1 << l) < 2 * max_points) ++l;
   return l;
 }
-static size_t raycast_smem_for(int max_points) {
-  return (size_t)HS_MAP_BYTES + 2 * sizeof(int) * ((size_t)1 << raycast_log2_hash(max_points)) + (size_t)max_points * sizeof(HsWalkRec) + (size_t)max_points * sizeof(HsBeamRec) + 2 * (size_t)max_points * sizeof(unsigned short) + 16;
+static size_t raycast_smem_for(int max_points, size_t map_bytes = HS_MAP_BYTES) {
+  return map_bytes + 2 * sizeof(int) * ((size_t)1 << raycast_log2_hash(max_points)) + (size_t)max_points * sizeof(HsWalkRec) + (size_t)max_points * sizeof(HsBeamRec) + 2 * (size_t)max_points * sizeof(unsigned short) + 16;
 }
 static size_t match2_smem_for(int max_points) {
   const size_t pitch = (size_t)(((max_points + 27) & ~31) + 4);   // hs_match2_pitch
   return HS_NPROD * pitch * sizeof(float) + (size_t)max_points * (sizeof(float4) + sizeof(float2) + sizeof(int) + sizeof(unsigned short)) + 16;
 }
-static size_t raycast_smem(const hs_engine* e) { return raycast_smem_for(e->P.max_points); }
+
+// The ray-cast launch: one CTA per (slot, level). Scans of up to 768 points: 384 threads, a 48 KB cell map, three CTAs per SM.
+// Longer scans (BASELINE configs[2]: 1440 beams) need ~80 KB of hash table and beam records per CTA, so only ONE CTA fits an
+// SM: it then takes the whole SM -- 1024 threads and a 144 KB map (590 k cells per band instead of 197 k).
+// Measured and dropped on B200 (configs[1]): the coarse levels as a second, concurrent launch of 128-thread CTAs with a 12 KB
+// map (k_raycast 163 -> 182 us: the small CTAs are slower than the slots they free).
+static bool raycast_big(const hs_engine* e) { return e->ray_big; }
+static int launch_raycast(hs_engine* e, const HsParams& Pc, int n, const int32_t* ids, const float2* points, const int32_t* counts,
+                          const float2* origos, cudaStream_t st) {
+  const int log2_hash = raycast_log2_hash(e->P.max_points);
+#ifdef HS_EXPERIMENTS
+  if (const char* ol = getenv("HSGPU_DEBUG_ONLY_LEVEL")) {   // timing experiment (wrong maps): one level's CTAs alone
+    const int l = atoi(ol);
+    k_raycast<HS_RAYCAST_THREADS, HS_MAP_BYTES, 3><<<n, HS_RAYCAST_THREADS, raycast_smem_for(e->P.max_points), st>>>(
+        Pc, n, ids, points, counts, origos, log2_hash, e->log2_seg_levels, l, 1);
+    return hs_launch_check(e);
+  }
+#endif
+  if (raycast_big(e))
+    k_raycast<HS_RAYCAST_THREADS_BIG, HS_MAP_BYTES_BIG, 1><<<n * e->P.n_levels, HS_RAYCAST_THREADS_BIG, raycast_smem_for(e->P.max_points, HS_MAP_BYTES_BIG), st>>>(
+        Pc, n, ids, points, counts, origos, log2_hash, e->log2_seg_levels, 0, e->P.n_levels);
+  else
+    k_raycast<HS_RAYCAST_THREADS, HS_MAP_BYTES, 3><<<n * e->P.n_levels, HS_RAYCAST_THREADS, raycast_smem_for(e->P.max_points), st>>>(
+        Pc, n, ids, points, counts, origos, log2_hash, e->log2_seg_levels, 0, e->P.n_levels);
+  return hs_launch_check(e);
+}
 static int warp_grid(int n_warps, int threads) { return (n_warps * 32 + threads - 1) / threads; }
 
 // GridMapLogOddsFunctions::probToLogOdds (HSL/map/GridMapLogOdds.h:198-203), host libm like the reference.
@@ -194,9 +222,11 @@ int hs_create(const hs_config* cfg, hs_engine** out) {
   HS_CK(cudaSetDevice(cfg->device));
 
   // smem budgets of the two per-scan kernels grow with max_points: refuse what the device cannot launch BEFORE allocating
+  int optin_smem = 0;
   {
     int optin = 0;
     HS_CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device));
+    optin_smem = optin;
     const size_t match_smem = cfg->max_points > 768 ? match2_smem_for(cfg->max_points)
                                                     : (size_t)hs_match2_pitch(cfg->max_points) * HS_NPROD * sizeof(float) + 6 * 4 * 160 * sizeof(float) + 256;
     if (raycast_smem_for(cfg->max_points) > (size_t)optin || match_smem > (size_t)optin) return HS_ERR_INVALID_ARG;
@@ -234,6 +264,7 @@ int hs_create(const hs_config* cfg, hs_engine** out) {
     }
     cudaGetLastError();
     if (const char* k = getenv("HSGPU_MATCH_L2_LEVELS")) P.l2_keep_levels = atoi(k);
+    if (const char* k = getenv("HSGPU_MATCH_SERIAL_SPREAD")) P.serial_spread = atoi(k) != 0;
     P.tail_slots = 2 * n_sm;   // measured on B200 (148 SMs): 0 -> 179 us, 148 -> 178, 296 -> 176, 444 -> 178.5, 600 -> 181
   }
   if (const char* pw = getenv("HSGPU_HD_PPW")) e->hd_ppw = atoi(pw);
@@ -360,21 +391,30 @@ int hs_create(const hs_config* cfg, hs_engine** out) {
     }
     int smem2 = (int)match2_smem_for(cfg->max_points);
     if (smem2 > 48 * 1024) {
-      cudaError_t e4 = cudaFuncSetAttribute(k_match2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
-      cudaError_t e5 = cudaFuncSetAttribute(k_match2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
-      if (e4 != cudaSuccess || e5 != cudaSuccess) {
+      cudaError_t e4 = cudaSuccess;
+#define HS_M2_ATTR(S_, T_) if (e4 == cudaSuccess) e4 = cudaFuncSetAttribute(k_match2<S_, T_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2)
+      HS_M2_ATTR(true, 128); HS_M2_ATTR(true, 256); HS_M2_ATTR(true, 512); HS_M2_ATTR(false, 128); HS_M2_ATTR(false, 256); HS_M2_ATTR(false, 512);
+#undef HS_M2_ATTR
+      if (e4 != cudaSuccess) {
         hs_destroy(e);
-        return (int)(e4 != cudaSuccess ? e4 : e5);
+        return (int)e4;
       }
     }
+    if (const char* mt = getenv("HSGPU_MATCH2_THREADS")) e->match2_threads = atoi(mt);
     int smem_r = (int)raycast_smem_for(cfg->max_points);  // k_raycast's cell map + hash table + beam records
-    if (smem_r > 48 * 1024) {
-      cudaError_t e3 = cudaFuncSetAttribute(k_raycast, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_r);
-      if (e3 != cudaSuccess) {
-        hs_destroy(e);
-        return (int)e3;
-      }
+    cudaError_t e3 = cudaFuncSetAttribute(k_raycast<HS_RAYCAST_THREADS, HS_MAP_BYTES, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_r);
+    // one CTA per SM anyway (more than half of the SM's shared memory per CTA): use the big-CTA instantiation if it fits
+    e->ray_big = (size_t)smem_r * 2 > (size_t)optin_smem && raycast_smem_for(cfg->max_points, HS_MAP_BYTES_BIG) <= (size_t)optin_smem;
+    if (const char* sp = getenv("HSGPU_RAYCAST_BIG")) e->ray_big = atoi(sp) != 0 && raycast_smem_for(cfg->max_points, HS_MAP_BYTES_BIG) <= (size_t)optin_smem;
+    if (e3 == cudaSuccess && e->ray_big)
+      e3 = cudaFuncSetAttribute(k_raycast<HS_RAYCAST_THREADS_BIG, HS_MAP_BYTES_BIG, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)raycast_smem_for(cfg->max_points, HS_MAP_BYTES_BIG));
+    if (e3 != cudaSuccess) {
+      hs_destroy(e);
+      return (int)e3;
     }
+    e->match_ct_pitch = 1;
+    if (const char* sp = getenv("HSGPU_MATCH_CT_PITCH")) e->match_ct_pitch = atoi(sp);
   }
   if (getenv("HSGPU_DEBUG_TIMES")) {   // timing experiments only
     if (cudaMalloc((void**)&P.dbg_times, ns * HS_MAX_LEVELS * 8 * sizeof(unsigned long long)) != cudaSuccess) P.dbg_times = nullptr;
@@ -555,10 +595,17 @@ static int run_update_device(hs_engine* e, int n, const int32_t* ids, const floa
     const int threads = HS_MATCH_THREADS;
     if (e->match_variant == 2) {
       const size_t smem2 = match2_smem_for(e->P.max_points);
-      if (e->P.strict)
-        k_match2<true><<<n, threads, smem2, st>>>(Pc, n, ids, (const float2*)points, counts, (const float2*)origos, hints, flags, mode);
-      else
-        k_match2<false><<<n, threads, smem2, st>>>(Pc, n, ids, (const float2*)points, counts, (const float2*)origos, hints, flags, mode);
+      // few long scans: more threads per scan (measured on B200, 256 x 1440 points: see DESIGN.md)
+      int t2 = n >= 4 * e->sm_count ? 128 : (n >= 2 * e->sm_count ? 256 : 512);
+      if (e->match2_threads == 128 || e->match2_threads == 256 || e->match2_threads == 512) t2 = e->match2_threads;
+#define HS_LAUNCH_MATCH2(STRICT_)                                                                                                          \
+  do {                                                                                                                                     \
+    if (t2 == 512) k_match2<STRICT_, 512><<<n, 512, smem2, st>>>(Pc, n, ids, (const float2*)points, counts, (const float2*)origos, hints, flags, mode); \
+    else if (t2 == 256) k_match2<STRICT_, 256><<<n, 256, smem2, st>>>(Pc, n, ids, (const float2*)points, counts, (const float2*)origos, hints, flags, mode); \
+    else k_match2<STRICT_, 128><<<n, 128, smem2, st>>>(Pc, n, ids, (const float2*)points, counts, (const float2*)origos, hints, flags, mode); \
+  } while (0)
+      if (e->P.strict) HS_LAUNCH_MATCH2(true); else HS_LAUNCH_MATCH2(false);
+#undef HS_LAUNCH_MATCH2
     } else {
     int ppt = (e->P.max_points + threads - 1) / threads;   // register-resident points (+ cell caches) per thread
     ppt = ppt <= 2 ? 2 : (ppt <= 3 ? 3 : (ppt <= 6 ? 6 : 0));
@@ -575,6 +622,8 @@ static int run_update_device(hs_engine* e, int n, const int32_t* ids, const floa
 #define HS_LAUNCH_MATCH_S(STRICT_)                                    \
   do {                                                                \
     if (ppt == 2) HS_LAUNCH_MATCH(STRICT_, 2);                        \
+    else if (ppt == 3 && wc && e->match_ct_pitch && hs_match2_pitch(e->P.max_points) == 388)                                      \
+      k_match<STRICT_, 3, 1, 388><<<n, threads, smem, st>>>(Pc, n, ids, (const float2*)points, counts, (const float2*)origos, hints, flags, mode); \
     else if (ppt == 3) HS_LAUNCH_MATCH(STRICT_, 3);                   \
     else if (ppt == 6) HS_LAUNCH_MATCH(STRICT_, 6);                   \
     else HS_LAUNCH_MATCH(STRICT_, 0);                                 \
@@ -591,10 +640,9 @@ static int run_update_device(hs_engine* e, int n, const int32_t* ids, const floa
     Pc.reverse_order = e->ray_alternate ? (int)(e->ray_launches++ & 1u) : 0;
     {
       ProfScope ps(e, HS_K_RAYCAST);
-      k_raycast<<<n * e->P.n_levels, HS_RAYCAST_THREADS, raycast_smem(e), st>>>(
-          Pc, n, ids, (const float2*)points_ray, counts_ray, (const float2*)origos, raycast_log2_hash(e->P.max_points), e->log2_seg_levels);
+      int rc = launch_raycast(e, Pc, n, ids, (const float2*)points_ray, counts_ray, (const float2*)origos, st);
+      if (rc != HS_OK) return rc;
     }
-    HS_LAUNCHED(e);
   }
   e->updates += (uint64_t)n;
   return HS_OK;
@@ -1227,10 +1275,9 @@ static int integrate_host(hs_engine* e, int n, const int32_t* stream_ids, const 
   HS_LAUNCHED(e);
   {
     ProfScope ps(e, HS_K_RAYCAST);
-    k_raycast<<<n * e->P.n_levels, HS_RAYCAST_THREADS, raycast_smem(e), e->stream>>>(
-        e->P, n, d_ids, (const float2*)e->d_points, e->d_counts, d_or, raycast_log2_hash(e->P.max_points), e->log2_seg_levels);
+    int rc = launch_raycast(e, e->P, n, d_ids, (const float2*)e->d_points, e->d_counts, d_or, e->stream);
+    if (rc != HS_OK) return rc;
   }
-  HS_LAUNCHED(e);
   HS_CK(cudaStreamSynchronize(e->stream));
   return HS_OK;
 }

@@ -57,6 +57,7 @@ struct HsParams {
   int hyp_stream;
   float* host_pose_out;             // non-NULL: the caller's pinned poses_out [slot][3]; the matcher's tail writes the pose there too
   int n_sm;                         // SM count of the device
+  int serial_spread;                // k_match: 1 = the serial warps of the CTAs sharing an SM use two sub-partitions instead of one
   int reverse_order;                // k_raycast: this launch walks the slots from the last to the first
   int l2_keep_levels;               // bit l: the matcher's gathers on level l carry an L2 evict-last hint
   int tail_slots;                   // k_raycast: the last `tail_slots` slots of a launch are dispatched level-major
@@ -602,29 +603,38 @@ __device__ __forceinline__ void hs_match_tail(const HsParams& P, int slot, int s
 
 // 7 CTAs per SM (<= 72 registers) keeps all 1024 streams of BASELINE configs[1] resident in ONE wave on 148 SMs; at 73+
 // registers the launch needs a second wave and takes 1.5x as long (measured: 94 -> 140 us).
-template <bool STRICT, int PPT, int WC>
+// PITCH > 0: the pitch of the product rows is a compile-time constant (the engine instantiates 388 = scans of 357..384 points,
+// BASELINE's 360-beam configurations): the nine stores per point and the chain's loads then address shared memory with
+// immediates. The per-warp miss lists and the expf table sit IN FRONT of the products at offsets that depend on PPT only.
+template <bool STRICT, int PPT, int WC, int PITCH = 0>
 __global__ void __launch_bounds__(HS_MATCH_THREADS, (PPT > 0 && PPT <= 3) ? 7 : 1) k_match(HsParams P, int n_slots, const int32_t* __restrict__ stream_ids,
                                                             const float2* __restrict__ points, const int32_t* __restrict__ counts,
                                                             const float2* __restrict__ origos, const float* __restrict__ hints,
                                                             const uint8_t* __restrict__ mwm_flags, int mode) {
-  extern __shared__ __align__(16) float hs_prod[];
+  extern __shared__ __align__(16) float hs_sm[];
   __shared__ float s_est[5];  // ex, ey, eth, sin(eth), cos(eth)
   __shared__ HsLevel s_lv;    // the current level's limx, limy, pt_factor, sx, max_iter (the other fields are not copied)
   __shared__ const float* s_val;   // ... and the first cell of its log-odds plane
   const int slot = P.slot0 + blockIdx.x;
   const int tid = threadIdx.x;
   if ((int)blockIdx.x >= n_slots) return;
-  // WC: behind the products, per warp PPT*128 floats (probabilities) and PPT*32 ints (block addresses), then the expf table
-  const int wc_ppt = PPT > 0 ? PPT : 1;
-  float* w_prob = hs_prod + HS_NPROD * hs_match2_pitch(P.max_points) + (tid >> 5) * (wc_ppt * 128);
-  int* w_addr = reinterpret_cast<int*>(hs_prod + HS_NPROD * hs_match2_pitch(P.max_points) + (HS_MATCH_THREADS / 32) * (wc_ppt * 128)) + (tid >> 5) * (wc_ppt * 32);
-  uint64_t* s_tab = reinterpret_cast<uint64_t*>(hs_prod + HS_NPROD * hs_match2_pitch(P.max_points) + (HS_MATCH_THREADS / 32) * (wc_ppt * 160));
+  // dynamic shared memory: WC: 32 x 8 B expf table | per warp PPT*32 ints (block addresses) | per warp PPT*128 floats
+  // (probabilities) -- then the products, 9 rows of `pitch` floats
+  constexpr int wc_ppt = PPT > 0 ? PPT : 1;
+  constexpr int n_warps_ct = HS_MATCH_THREADS / 32;
+  constexpr int aux_floats = WC ? 64 + n_warps_ct * wc_ppt * 160 : 0;
+  const int pitch = PITCH > 0 ? PITCH : hs_match2_pitch(P.max_points);
+  uint64_t* s_tab = reinterpret_cast<uint64_t*>(hs_sm);
+  int* w_addr = reinterpret_cast<int*>(hs_sm + 64) + (tid >> 5) * (wc_ppt * 32);
+  float* w_prob = hs_sm + 64 + n_warps_ct * wc_ppt * 32 + (tid >> 5) * (wc_ppt * 128);
+  float* hs_prod = hs_sm + aux_floats;
   if (WC && tid < 32) s_tab[tid] = hs_exp2f_tab_dev[tid];   // visible after the first __syncthreads below
   // the serial part (sums, 3x3 solve, sin/cos) is carried by ONE warp, chosen by the CTA index. CTAs are dealt out to the
   // SMs breadth first and 148 = 0 mod 4, so the CTAs sharing an SM pick the SAME warp number and their serial warps share
   // one SM sub-partition (warp w issues from scheduler w mod 4), where their 4-cycle FADD chains interleave. Measured on
   // B200: spreading them over the four sub-partitions ((blockIdx + blockIdx / n_sm) & 3) costs 5-8 us per launch.
-  const int sw = blockIdx.x & ((blockDim.x >> 5) - 1);
+  // P.serial_spread = 1: the CTAs of an SM alternate between two warp numbers (two sub-partitions carry the chains)
+  const int sw = (P.serial_spread ? (blockIdx.x ^ ((blockIdx.x / (unsigned)P.n_sm) & 1u)) : blockIdx.x) & ((blockDim.x >> 5) - 1);
   const bool serial = (tid >> 5) == sw, leader = tid == (sw << 5);
   const bool hyp = P.hyp_pose != nullptr;
   const int s = hyp ? P.hyp_stream : hs_slot_stream(stream_ids, slot);
@@ -699,7 +709,7 @@ __global__ void __launch_bounds__(HS_MATCH_THREADS, (PPT > 0 && PPT <= 3) ? 7 : 
         const bool keep_l2 = ((P.l2_keep_levels >> level) & 1) != 0;
         for (int it = 0; it <= max_iter; ++it) {  // 1 + maxIterations evaluations, no early exit
           const float cex = s_est[0], cey = s_est[1], csn = s_est[3], ccs = s_est[4];
-          a = hs_eval_cta<STRICT, PPT, WC>(val, L, cex, cey, csn, ccs, pts, preg, cache, n, L.pt_factor, hs_prod, hs_match2_pitch(P.max_points), sw, &mt,
+          a = hs_eval_cta<STRICT, PPT, WC>(val, L, cex, cey, csn, ccs, pts, preg, cache, n, L.pt_factor, hs_prod, pitch, sw, &mt,
                                            w_addr, w_prob, s_tab, i0, istride, keep_l2);
           if (serial) {
             clamps += hs_gauss_newton_step(a, ex, ey, eth) ? 1u : 0u;
@@ -867,8 +877,10 @@ __device__ __forceinline__ HsAcc hs_eval_cta2(const float* __restrict__ val, con
   return a;
 }
 
-template <bool STRICT>
-__global__ void __launch_bounds__(HS_MATCH_THREADS) k_match2(HsParams P, int n_slots, const int32_t* __restrict__ stream_ids,
+// THREADS per CTA: 128 when there are enough scans to fill the device with one 4-warp CTA each, 512 for small batches of long
+// scans (BASELINE configs[2]: 256 scans of 1440 points on 148 SMs) -- the point phases scale with the threads, the chains do not.
+template <bool STRICT, int THREADS>
+__global__ void __launch_bounds__(THREADS, 2) k_match2(HsParams P, int n_slots, const int32_t* __restrict__ stream_ids,
                                                              const float2* __restrict__ points, const int32_t* __restrict__ counts,
                                                              const float2* __restrict__ origos, const float* __restrict__ hints,
                                                              const uint8_t* __restrict__ mwm_flags, int mode) {
@@ -1383,8 +1395,11 @@ __global__ void __launch_bounds__(128) k_occupancy_ray(HsParams P, int stream, i
 
 #define HS_HASH_EMPTY (-1)
 #define HS_MAP_BYTES 49152                 // shared-memory cell map: 2 bits per cell, 16 cells per 32-bit word
-#define HS_MAP_CELLS (HS_MAP_BYTES * 4)    // low half-word: crossed by a free trace; high half-word: some beam's end cell
+                                           // (low half-word: crossed by a free trace; high half-word: some beam's end cell)
 #define HS_RAYCAST_THREADS 384
+// long scans (hash table + beam records of ~80 KB: one CTA per SM anyway): the CTA takes the whole SM
+#define HS_MAP_BYTES_BIG 147456
+#define HS_RAYCAST_THREADS_BIG 1024
 
 struct HsBeam {
   int valid;            // begin != end and both inside the grid
@@ -1495,13 +1510,16 @@ __device__ __forceinline__ void hs_free_hits_end_cell(const int* __restrict__ hk
 // | max_points * sizeof(HsBeamRec) | 2 * max_points * sizeof(unsigned short), T = hash_size (power of two >= 2 * max_points).
 // log2_seg_levels: the free-cell walk is cut into segments of 2^k steps that are dealt out evenly to the threads
 // (k = low byte on level 0, next byte on the coarser levels).
-__global__ void __launch_bounds__(HS_RAYCAST_THREADS, 3) k_raycast(HsParams P, int n_slots, const int32_t* __restrict__ stream_ids,
-                                                                const float2* __restrict__ points, const int32_t* __restrict__ counts,
-                                                                const float2* __restrict__ origos, int log2_hash, int log2_seg_levels) {
+template <int THREADS, int MAP_BYTES, int MIN_CTAS>
+__global__ void __launch_bounds__(THREADS, MIN_CTAS) k_raycast(HsParams P, int n_slots, const int32_t* __restrict__ stream_ids,
+                                                               const float2* __restrict__ points, const int32_t* __restrict__ counts,
+                                                               const float2* __restrict__ origos, int log2_hash, int log2_seg_levels,
+                                                               int level_first, int level_count) {
+  constexpr int MAP_CELLS = MAP_BYTES * 4;
   extern __shared__ __align__(16) unsigned char hs_smem[];
   const int hash_size = 1 << log2_hash, hash_mask = hash_size - 1;
   unsigned* cmap = reinterpret_cast<unsigned*>(hs_smem);                   // 16 cells per word: free bits | end bits << 16
-  int* hkeys = reinterpret_cast<int*>(hs_smem + HS_MAP_BYTES);             // end cell (grid offset) or EMPTY
+  int* hkeys = reinterpret_cast<int*>(hs_smem + MAP_BYTES);             // end cell (grid offset) or EMPTY
   int* hvals = hkeys + hash_size;                                          // (io << 1) | free-came-first flag
   HsWalkRec* walk = reinterpret_cast<HsWalkRec*>(hvals + hash_size);       // owner beams
   HsBeamRec* beams = reinterpret_cast<HsBeamRec*>(walk + P.max_points);
@@ -1520,17 +1538,19 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS, 3) k_raycast(HsParams P, i
   {
     // ... except for the last ~wave of slots, which is dispatched level-major (fine grids first): the launch then drains
     // through the short coarse-grid CTAs instead of waiting for a few long fine-grid ones
+    // this launch covers levels [level_first, level_first + level_count) of every slot
     const int n_tail = min(n_slots, P.tail_slots), n_head = n_slots - n_tail;
     int local;
-    if ((int)blockIdx.x < n_head * P.n_levels) {
-      local = blockIdx.x / P.n_levels;
-      level = blockIdx.x - local * P.n_levels;
+    if ((int)blockIdx.x < n_head * level_count) {
+      local = blockIdx.x / level_count;
+      level = blockIdx.x - local * level_count;
     } else {
-      const int r = blockIdx.x - n_head * P.n_levels;
+      const int r = blockIdx.x - n_head * level_count;
       level = r / n_tail;
       local = n_head + (r - level * n_tail);
     }
-    if (local >= n_slots || level >= P.n_levels) return;
+    if (local >= n_slots || level >= level_count) return;
+    level += level_first;
     // consecutive launches walk the slots in opposite directions: the grids of the streams integrated LAST by one launch
     // are still in L2 when the next launch starts with them
     if (P.reverse_order) local = n_slots - 1 - local;
@@ -1546,7 +1566,7 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS, 3) k_raycast(HsParams P, i
   float* val = P.val + (size_t)s_map * P.cells_per_stream + L.cell_offset;
   int* idx = P.idx + (size_t)s_map * P.cells_per_stream + L.cell_offset;
   const int W = L.sx;
-  const int T = blockDim.x;
+  constexpr int T = THREADS;   // == blockDim.x: divisions and strides by T compile to multiplications / immediates
 
   // level 0 integrates the scan itself, level i > 0 the container last refreshed by matchData
   // (MapRepMultiMap.h:134-147) -- possibly stale or empty when map_without_matching was used.
@@ -1592,7 +1612,7 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS, 3) k_raycast(HsParams P, i
   {   // ... and the whole cell map (8 16-byte stores per thread, while the prologue's global loads are in flight): the box
       // is not known yet, and phase A3 sets end-cell bits right after the next barrier
     uint4* m4 = reinterpret_cast<uint4*>(hs_smem);
-    for (int i = threadIdx.x; i < HS_MAP_BYTES / 16; i += T) m4[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = threadIdx.x; i < MAP_BYTES / 16; i += T) m4[i] = make_uint4(0u, 0u, 0u, 0u);
   }
   if (threadIdx.x == 0) { s_box[0] = INT_MAX; s_box[1] = INT_MAX; s_box[2] = INT_MIN; s_box[3] = INT_MIN; s_alloc = 0ULL; s_visits = 0u; }
   __syncthreads();
@@ -1642,7 +1662,7 @@ __global__ void __launch_bounds__(HS_RAYCAST_THREADS, 3) k_raycast(HsParams P, i
   const int bh = y1 - y0 + 1;
   const int pw = (((x1 - x0) >> 4) + 1) | 1;   // 16-cell words per map row
   const int pitch = pw << 4;                   // cells per map row
-  const int band_rows = min(bh, HS_MAP_CELLS / pitch);   // >= 1: hs_create limits the grid width
+  const int band_rows = min(bh, MAP_CELLS / pitch);   // >= 1: hs_create limits the grid width
   const int n_bands = (bh + band_rows - 1) / band_rows;
 
   const bool single_band = n_bands == 1;
