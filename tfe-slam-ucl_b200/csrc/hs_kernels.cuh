@@ -1463,6 +1463,11 @@ __device__ __forceinline__ unsigned hs_lds_u32(unsigned addr) {
 __device__ __forceinline__ void hs_reds_or(unsigned addr, unsigned v) {
   asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
+__device__ __forceinline__ unsigned hs_atoms_or(unsigned addr, unsigned v) {
+  unsigned old;
+  asm volatile("atom.shared.or.b32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
+  return old;
+}
 // shared-window address of a generic pointer, computed ONCE (volatile: the compiler may not re-derive it per use)
 __device__ __forceinline__ unsigned hs_shared_addr(const void* p) {
   unsigned a;
@@ -1835,13 +1840,14 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_raycast(HsParams P, int n
         for (; j < j1; ++j) {
           const int steps = min(seg, rem);
           for (int t = 0; t < steps; ++t) {
+            // ONE shared-memory atomic per step: it sets the free bit unconditionally and returns the word, whose end bit says
+            // whether the cell is some beam's end point. (The load / test / conditional-reduction form cost 8 more instructions
+            // per step, and near the sensor, where most cells are already marked by other beams, nearly every warp iteration ran
+            // both sides of the test: 27 lanes -> 16 + 11, ncu.) A free bit that lands on an end cell is masked out by the sweep.
             const unsigned waddr = cmap_s + (((unsigned)k >> 4) << 2);
-            const unsigned word = hs_lds_u32(waddr);
-            const unsigned mbit = 0x10001u << ((unsigned)k & 15u);
-            const unsigned hit = word & mbit;
-            if (hit == 0u) {
-              hs_reds_or(waddr, mbit & 0xFFFFu);
-            } else if (hit & 0xFFFF0000u) {   // the free trace crosses a cell that is some beam's end point
+            const unsigned fbit = 1u << ((unsigned)k & 15u);
+            const unsigned word = hs_atoms_or(waddr, fbit);
+            if (word & (fbit << 16)) {   // the free trace crosses a cell that is some beam's end point (rare)
               int xx;
               const int yy = hs_udiv_small(k, pitch, xx);   // k < 2^18, pitch < 2^15: exact
               hs_free_hits_end_cell(hkeys, hvals, hash_mask, log2_hash, (yy + yb0) * W + (xx + x0), beam);
@@ -1890,7 +1896,8 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_raycast(HsParams P, int n
       const int ry0 = hs_udiv_small(threadIdx.x, qpr, c);
       int ni = ry0 * (pw << 2) + c, gq = (yb0 + ry0) * W + x0 + (c << 2);
       for (int q0 = threadIdx.x; q0 < nq; q0 += T) {
-        const unsigned bits = (cmap[ni >> 2] >> ((unsigned)(ni & 3) << 2)) & 0xFu;
+        const unsigned mw = cmap[ni >> 2];
+        const unsigned bits = ((mw & ~(mw >> 16)) >> ((unsigned)(ni & 3) << 2)) & 0xFu;   // free and not an end cell
         if (bits) {
           // val += f on the marked cells of the quad as ONE 16-byte floating-point reduction performed in L2 (IEEE round to
           // nearest, like the FADD of updateSetFree; nothing is loaded into or written back from registers). Unmarked cells
@@ -1917,7 +1924,8 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_raycast(HsParams P, int n
         const int row = (yb0 + ry) * W + x0 + lane;
         const unsigned* mrow = cmap + ry * pw + (lane >> 4);
         for (int sg = 0; sg < segs; ++sg) {
-          const bool on = (x0 + (sg << 5) + lane <= x1) && ((mrow[sg * 2] >> (lane & 15)) & 1u);
+          const unsigned mw = mrow[sg * 2];
+          const bool on = (x0 + (sg << 5) + lane <= x1) && (((mw & ~(mw >> 16)) >> (lane & 15)) & 1u);   // free and not an end cell
           if (on) {
             val[row + (sg << 5)] = val[row + (sg << 5)] + f;
             idx[row + (sg << 5)] = mark_free;
