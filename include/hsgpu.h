@@ -61,7 +61,9 @@ typedef struct {
 
 /* ---- lifetime / configuration ---------------------------------------------------------- */
 
-/* HectorSlamProcessor ctor + MapRepMultiMap ctor (HSL/slam_main/MapRepMultiMap.h:48-72). */
+/* HectorSlamProcessor ctor + MapRepMultiMap ctor (HSL/slam_main/MapRepMultiMap.h:48-72).
+ * Process-wide side effect: if the device's cudaLimitPersistingL2CacheSize is 0, it is raised to 16 MB (the matcher's
+ * evict-last gathers live there; HSGPU_L2_PERSIST_MB sets another size, a limit the process has already chosen is kept). */
 int hs_create(const hs_config* cfg, hs_engine** out);
 /* ~HectorSlamProcessor (HectorSlamProcessor.h:66-69). */
 int hs_destroy(hs_engine* e);
@@ -110,7 +112,9 @@ const char* hs_status_string(int status);
  * stream_ids and cov_out are NULL, the call returns as soon as the poses are in poses_out; this batch's updateByScan keeps
  * running on the engine's stream, every later call on the engine (another update, a map or pose read, hs_synchronize) is
  * ordered behind it, and the input buffers may be reused on return. The next call's points are then fetched while that
- * integration runs. HSGPU_E2E_DEFER=0 restores "returns after the integration". */
+ * integration runs. HSGPU_E2E_DEFER=0 restores "returns after the integration". Consequence for device-resident consumers:
+ * work the caller launches on ANOTHER CUDA stream (a kernel reading hs_device_pose_ptr, a peer copy of the grids) is not
+ * ordered behind the deferred integration -- call hs_synchronize first, or run it on the stream given to hs_set_cuda_stream. */
 int hs_update_batch(hs_engine* e, int n, const int32_t* stream_ids, const float* points, const int32_t* counts,
                     const float* origos, const float* pose_hints, const uint8_t* map_without_matching,
                     float* poses_out, float* cov_out);

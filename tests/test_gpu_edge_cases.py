@@ -133,6 +133,15 @@ def test_ranges_entry_point_equals_points_entry_point(hs, oracle):
             assert np.array_equal(bits(out[s]), bits(ref)), (k, s)
     assert_same_maps(eng, procs, 3)
     eng.close()
+    # beam counts that are not a multiple of 4 take the kernel's scalar path (the 360-beam case above takes the float4 path)
+    for nb in (359, 358, 5):
+        with hs.Engine(n_streams=n, max_points=360) as e2, hs.Engine(n_streams=n, max_points=360) as e3:
+            e2.set_scan_geometry(nb, sc.angle_min, sc.angle_increment, sc.range_min, sc.range_max)
+            for k in range(3):
+                out, _ = e2.update_batch_ranges(ranges[k][:, :nb])
+                p2, c2 = hs.scan_to_points_host(ranges[k][:, :nb], sc, 20.0, max_points=360)
+                ref, _ = e3.update_batch(p2, c2)
+                assert np.array_equal(bits(out), bits(ref)), (nb, k)
 
 
 def test_large_bounding_box_is_processed_in_bands(hs, oracle):

@@ -344,6 +344,9 @@ def test_multi_start_match_hypotheses(hs, oracle):
                 assert np.array_equal(bits(gcov[i]), bits(c)), i
                 n_ok += 1
         assert n_ok > n_hyp * 0.9
+        # small batches take the matcher's ordinary gather path (no probability block planes): same bits
+        few, fcov = eng.match_hypotheses(1, scan, hints[:9])
+        assert np.array_equal(bits(few), bits(got[:9])) and np.array_equal(bits(fcov), bits(gcov[:9]))
         # the hypotheses near the true pose converge onto the matcher's own answer for that scan
         ref_pose = cpu.update(pts[n_scans, 1], cnt[n_scans, 1], hint=cpu.pose())
         near = np.linalg.norm(hints[:, :2] - pose[None, :2], axis=1) < 0.05

@@ -69,6 +69,7 @@ struct hs_engine {
   uint64_t pblk_epoch, map_epoch;          // map_epoch: bumped whenever cells of any stream may have been written
   int hd_ppw;                              // HSGPU_HD_PPW: poses per warp in k_hessian_derivs (0 = by batch size)
   int match_ct_pitch;                      // HSGPU_MATCH_CT_PITCH (A/B): use the compile-time-pitch instantiation of k_match when it applies
+  int hyp_use_pblk;                        // HSGPU_HYP_PBLK (A/B): multi-start matching through the probability block planes
   int match2_threads;                      // HSGPU_MATCH2_THREADS: 128 / 256 / 512 threads per k_match2 CTA (0 = by batch size)
   int ray_big;                             // k_raycast as one 1024-thread CTA per SM with a 144 KB map (long scans, launch_raycast)
   void* h_pinned;                          // engine-owned pinned host staging (ensure_pinned)
@@ -413,6 +414,8 @@ int hs_create(const hs_config* cfg, hs_engine** out) {
       hs_destroy(e);
       return (int)e3;
     }
+    e->hyp_use_pblk = 1;
+    if (const char* sp = getenv("HSGPU_HYP_PBLK")) e->hyp_use_pblk = atoi(sp);
     e->match_ct_pitch = 1;
     if (const char* sp = getenv("HSGPU_MATCH_CT_PITCH")) e->match_ct_pitch = atoi(sp);
   }
@@ -622,6 +625,8 @@ static int run_update_device(hs_engine* e, int n, const int32_t* ids, const floa
 #define HS_LAUNCH_MATCH_S(STRICT_)                                    \
   do {                                                                \
     if (ppt == 2) HS_LAUNCH_MATCH(STRICT_, 2);                        \
+    else if (ppt == 3 && wc && Pc.hyp_pblk)                                                                                        \
+      k_match<STRICT_, 3, 2, 0><<<n, threads, smem, st>>>(Pc, n, ids, (const float2*)points, counts, (const float2*)origos, hints, flags, mode); \
     else if (ppt == 3 && wc && e->match_ct_pitch && hs_match2_pitch(e->P.max_points) == 388)                                      \
       k_match<STRICT_, 3, 1, 388><<<n, threads, smem, st>>>(Pc, n, ids, (const float2*)points, counts, (const float2*)origos, hints, flags, mode); \
     else if (ppt == 3) HS_LAUNCH_MATCH(STRICT_, 3);                   \
@@ -1238,13 +1243,19 @@ int hs_match_hypotheses(hs_engine* e, int stream, const float* points, int n_poi
   HS_CK(cudaMemcpyAsync(base + o_hint, pose_hints, b_h, cudaMemcpyHostToDevice, e->stream));
   HS_CK(cudaMemsetAsync(base + o_cov, 0, b_c, e->stream));   // an empty scan leaves the covariance untouched (ScanMatcher.h:189)
   e->h2d_bytes += (size_t)n_points * 8 + 4 + b_h;
+  // thousands of hypotheses read one stream's maps: the register-cache matcher takes its 2x2 blocks from the stream's
+  // probability block planes (one conversion per cell for all of them, ensure_pblk) -- 360-point-class scans only
+  const bool use_pblk = e->match_variant == 3 && (e->P.max_points + HS_MATCH_THREADS - 1) / HS_MATCH_THREADS == 3 && n_hyp >= 64 && e->hyp_use_pblk;
+  if (use_pblk && (st = ensure_pblk(e, stream)) != HS_OK) return st;
   const int saved_stream = e->P.hyp_stream;
+  e->P.hyp_pblk = use_pblk ? e->pblk : nullptr;
   e->P.hyp_pose = (float*)(base + o_pose);
   e->P.hyp_cov = (float*)(base + o_cov);
   e->P.hyp_stream = stream;
   st = run_update_device(e, n_hyp, nullptr, (const float*)base, (const int32_t*)(base + o_cnt), nullptr, (const float*)(base + o_hint), nullptr, 1);
   e->P.hyp_pose = nullptr;
   e->P.hyp_cov = nullptr;
+  e->P.hyp_pblk = nullptr;
   e->P.hyp_stream = saved_stream;
   e->updates -= (uint64_t)n_hyp;   // hypotheses are not stream updates
   if (st != HS_OK) return st;

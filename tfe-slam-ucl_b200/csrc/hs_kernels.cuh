@@ -55,6 +55,7 @@ struct HsParams {
   float* hyp_pose;
   float* hyp_cov;
   int hyp_stream;
+  const float4* hyp_pblk;           // ... WC == 2 instantiation: the stream's probability block planes (k_build_pblk) instead of val
   float* host_pose_out;             // non-NULL: the caller's pinned poses_out [slot][3]; the matcher's tail writes the pose there too
   int n_sm;                         // SM count of the device
   int serial_spread;                // k_match: 1 = the serial warps of the CTAs sharing an SM use two sub-partitions instead of one
@@ -138,7 +139,8 @@ __device__ __forceinline__ bool hs_pose_difference_larger_than(float x1, float y
 // One warp per scan; beam_cs holds (cosf(angle_i), sinf(angle_i)) with angle_i the reference's float
 // accumulation, precomputed on the host when the scan geometry is set. Valid beams are compacted in
 // order (ballot + popc), as the reference's push_back loop does.
-#define HS_SCAN_INFLIGHT 12   // 384 beams per pass
+#define HS_SCAN_INFLIGHT 12   // 384 beams per pass (scalar path)
+#define HS_SCAN_INFLIGHT4 3   // 3 x 128 beams per pass (float4 path)
 __global__ void __launch_bounds__(128) k_scan_to_points(const float* __restrict__ ranges, int n_slots, int n_beams,
                                                         const float2* __restrict__ beam_cs, float range_min,
                                                         float max_range_for_container, float scale_to_map, int max_points,
@@ -149,6 +151,52 @@ __global__ void __launch_bounds__(128) k_scan_to_points(const float* __restrict_
   const float* r = ranges + (size_t)warp * n_beams;
   float2* out = points + (size_t)warp * max_points;
   int base = 0;
+  if ((n_beams & 3) == 0 && (reinterpret_cast<uintptr_t>(ranges) & 15) == 0) {
+    // float4 path: a lane owns 4 consecutive beams (16-byte range loads, 32-byte cos/sin loads); the ordered compaction is a
+    // warp prefix sum over the lanes' valid counts plus the position inside the lane
+    const float4* r4 = reinterpret_cast<const float4*>(r);
+    const float4* cs4 = reinterpret_cast<const float4*>(beam_cs);   // two (cos, sin) pairs per float4
+    const int n4 = n_beams >> 2;
+    for (int c0 = 0; c0 < n4; c0 += 32 * HS_SCAN_INFLIGHT4) {
+      float4 d_in[HS_SCAN_INFLIGHT4];
+#pragma unroll
+      for (int u = 0; u < HS_SCAN_INFLIGHT4; ++u) {   // all loads of a chunk first: `ranges` may be pinned host memory (zero-copy)
+        const int q = c0 + u * 32 + lane;
+        d_in[u] = q < n4 ? r4[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < HS_SCAN_INFLIGHT4; ++u) {
+        const int q = c0 + u * 32 + lane;
+        const float d[4] = {d_in[u].x, d_in[u].y, d_in[u].z, d_in[u].w};
+        unsigned vm = 0u;
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+          if (q < n4 && d[t] > range_min && d[t] < max_range_for_container) vm |= 1u << t;
+        const int mine = __popc(vm);
+        int incl = mine;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, incl, s);
+          if (lane >= s) incl += t;
+        }
+        int pos = base + incl - mine;
+        if (vm) {
+          const float4 ca = cs4[2 * q], cb = cs4[2 * q + 1];
+          const float cx[4] = {ca.x, ca.z, cb.x, cb.z}, sy[4] = {ca.y, ca.w, cb.y, cb.w};
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            if (vm & (1u << t)) {
+              const float dd = d[t] * scale_to_map;
+              if (pos < max_points) out[pos] = make_float2(cx[t] * dd, sy[t] * dd);
+              ++pos;
+            }
+        }
+        base += __shfl_sync(0xffffffffu, incl, 31);
+      }
+    }
+    if (lane == 0) counts[warp] = base < max_points ? base : max_points;
+    return;
+  }
   for (int c0 = 0; c0 < n_beams; c0 += 32 * HS_SCAN_INFLIGHT) {
     // all loads of a chunk are issued before the first is used: `ranges` may be the caller's pinned host buffer read over
     // PCIe (zero-copy), where one round trip costs microseconds
@@ -367,7 +415,9 @@ __device__ __forceinline__ unsigned long long hs_policy_evict_last() {
 // consecutive lanes = the four corners of one block), and the owners read their four probabilities back as one float4.
 // Same values, same order of the per-point arithmetic; only who computes a probability changes.
 //   w_addr: this warp's PPT*32 ints, w_prob: this warp's PPT*128 floats (16-byte aligned), s_tab: expf table in shared memory
-template <int PPT>
+// PB: `val` is not the log-odds plane but the level's probability BLOCK plane (k_build_pblk; multi-start matching, where
+// thousands of hypotheses read one stream's maps): a miss is one 16-byte load of the finished 2x2 block, no dense pass.
+template <int PPT, bool PB = false>
 __device__ __forceinline__ void hs_points_phase_wc(const float* __restrict__ val, const HsLevel& L, float ex, float ey, float sn, float cs,
                                                    const float2* preg, HsCellCache* cache, int n, float pt_factor,
                                                    float* __restrict__ prod, int pitch, int* __restrict__ w_addr,
@@ -389,6 +439,13 @@ __device__ __forceinline__ void hs_points_phase_wc(const float* __restrict__ val
       const int k = (int)qy * L.sx + (int)qx;
       if (k != cache[j].key) { cache[j].key = k; m = true; }
     }
+    if (PB) {
+      if (m) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(val) + cache[j].key);
+        cache[j].p0 = b.x; cache[j].p1 = b.y; cache[j].p2 = b.z; cache[j].p3 = b.w;
+      }
+      continue;
+    }
     bal[j] = __ballot_sync(0xffffffffu, m);
     if (m) {
       mine |= 1u << j;
@@ -396,7 +453,7 @@ __device__ __forceinline__ void hs_points_phase_wc(const float* __restrict__ val
     }
     total += __popc(bal[j]);
   }
-  if (total) {   // warp-uniform
+  if (!PB && total) {   // warp-uniform
     __syncwarp();
     // item = (miss, corner): lane l always handles corner l & 3 of miss (l >> 2) + 8 * round
     const int coff = (lane & 1) + ((lane & 2) ? L.sx : 0);
@@ -466,7 +523,7 @@ __device__ __forceinline__ HsAcc hs_eval_cta(const float* __restrict__ val, cons
                                              int i0 = 0, int istride = 0, bool keep_in_l2 = false) {
   if (PPT > 0 && WC) {
     if ((i0 & ~31) < n)   // warp-uniform (the phase uses full-warp ballots): skip warps whose first point is past the scan
-      hs_points_phase_wc<(PPT > 0 ? PPT : 1)>(val, L, ex, ey, sn, cs, preg, cache, n, pt_factor, prod, pitch, w_addr, w_prob, s_tab, i0, istride, keep_in_l2);
+      hs_points_phase_wc<(PPT > 0 ? PPT : 1), WC == 2>(val, L, ex, ey, sn, cs, preg, cache, n, pt_factor, prod, pitch, w_addr, w_prob, s_tab, i0, istride, keep_in_l2);
   } else if (PPT > 0) {
 #pragma unroll
     for (int j = 0; j < (PPT > 0 ? PPT : 1); ++j) {
@@ -598,7 +655,8 @@ __device__ __forceinline__ void hs_match_tail(const HsParams& P, int slot, int s
 // (sums, 3x3 solve, sin/cos of the new angle); the other warps only help with the per-point gathers.
 // mode: 0 = update (match + gate), 1 = match only (no gate, no integration).
 // dynamic shared memory: 9 * pitch floats (products, sum-major) | WC: per warp PPT*128 floats + PPT*32 ints | WC: 32 x 8 B expf table.
-// WC = 1: the cache misses of a warp are processed densely (hs_points_phase_wc); 0: every thread converts its own misses.
+// WC = 1: the cache misses of a warp are processed densely (hs_points_phase_wc); 0: every thread converts its own misses;
+// 2 (multi-start matching only): misses are single 16-byte loads from the stream's probability block planes.
 #define HS_MATCH_THREADS 128   // measured on B200 at 1024 streams: 64 -> 160 us, 96 -> 122, 128 -> 109, 192/256 -> 143 per launch
 
 // 7 CTAs per SM (<= 72 registers) keeps all 1024 streams of BASELINE configs[1] resident in ONE wave on 148 SMs; at 73+
@@ -699,7 +757,7 @@ __global__ void __launch_bounds__(HS_MATCH_THREADS, (PPT > 0 && PPT <= 3) ? 7 : 
             // the kernel (13.5 % of the stall samples) -- and the plane pointer was re-derived inside the miss loop. Same-box
             // A/B on B200, 1024 streams: 99.1 us (constant bank) -> 96.0 (level fields here) -> 95.6 (+ the plane pointer)
             s_lv.limx = Lc.limx; s_lv.limy = Lc.limy; s_lv.pt_factor = Lc.pt_factor; s_lv.sx = Lc.sx; s_lv.max_iter = Lc.max_iter;
-            s_val = val_s + Lc.cell_offset;
+            s_val = WC == 2 ? reinterpret_cast<const float*>(P.hyp_pblk + Lc.cell_offset) : val_s + Lc.cell_offset;
           }
         }
         __syncthreads();
@@ -1137,12 +1195,13 @@ __global__ void __launch_bounds__(HS_HD_THREADS) k_hessian_derivs(const float4* 
 #pragma unroll
         for (int k = 0; k < HS_NPROD; ++k) part[j][k] = 0.0f;
     }
-    for (int c0 = 0; c0 < n_pts; c0 += HS_HD_CHUNK) {
-      const int len = min(HS_HD_CHUNK, n_pts - c0);
-      // point phase, step 1: block addresses, all loads in flight
-      float4 blk[PPW][R];
-      float fxs[PPW][R], fys[PPW][R];
-      unsigned inside = 0u;
+    // software pipeline over the chunks: the block loads of chunk c+1 are issued BEFORE the chain phase of chunk c, so the L2
+    // round trip of the gathers hides behind the serial adds instead of preceding them
+    float4 blk[PPW][R];
+    float fxs[PPW][R], fys[PPW][R];
+    unsigned inside = 0u;
+    auto gather = [&](int c0) {   // point phase, step 1: block addresses of chunk c0, all loads in flight
+      inside = 0u;
 #pragma unroll
       for (int j = 0; j < PPW; ++j) {
 #pragma unroll
@@ -1163,7 +1222,11 @@ __global__ void __launch_bounds__(HS_HD_THREADS) k_hessian_derivs(const float4* 
           }
         }
       }
-      // step 2: terms and products
+    };
+    gather(0);
+    for (int c0 = 0; c0 < n_pts; c0 += HS_HD_CHUNK) {
+      const int len = min(HS_HD_CHUNK, n_pts - c0);
+      // step 2: terms and products of chunk c0
 #pragma unroll
       for (int j = 0; j < PPW; ++j) {
 #pragma unroll
@@ -1183,6 +1246,7 @@ __global__ void __launch_bounds__(HS_HD_THREADS) k_hessian_derivs(const float4* 
           }
         }
       }
+      if (c0 + HS_HD_CHUNK < n_pts) gather(c0 + HS_HD_CHUNK);   // in flight during the chain phase below
       if (STRICT) {
         __syncwarp();
         if (lane < PPW * HS_NPROD) {
