@@ -49,13 +49,13 @@ def launches(tag, path):
             cur = collections.OrderedDict()
             legs.append(cur)
         cur.setdefault(name, []).append(us)
-    leg_names = ["inputs resident in HBM (bench `value`, `roofline`)", "hs_update_batch, pinned host buffers, deferred integration (bench `e2e`)",
+    leg_names = ["inputs resident in HBM (bench `value`, `roofline`)", "hs_update_batch, pinned host buffers, deferred integration (bench `e2e`: warm-up + R repeats of the K-step loop)",
                  "hs_update_batch_ranges (bench `e2e.ranges_api`)", "hs_submit_batch / hs_wait, DMA on a copy stream (bench `e2e.pipelined_api`)"]
     with open(os.path.join(HERE, tag + "_launches.md"), "w") as f:
         f.write("# %s: every launch with its device time (ncu --metrics gpu__time_duration.sum --clock-control none)\n\n" % tag)
         f.write("Times are cold-cache and serialised by the profiler: compare SHARES with bench.py's CUDA-event shares, not absolutes.\n")
         for li, agg in enumerate(legs):
-            hot = {k: v for k, v in agg.items() if k.startswith(("k_match", "void k_match", "k_raycast", "k_scan_to_points", "k_cloud_to_points"))}
+            hot = {k: v for k, v in agg.items() if k.replace("void ", "").startswith(("k_match", "k_raycast", "k_scan_to_points", "k_cloud_to_points"))}
             tot = sum(sum(v) for v in hot.values()) or 1.0
             f.write("\n## leg %d: %s\n\n" % (li + 1, leg_names[li] if li < len(leg_names) else "further launches"))
             f.write("| kernel | launches | avg us | min us | max us | share of hot-path time |\n|---|---|---|---|---|---|\n")
