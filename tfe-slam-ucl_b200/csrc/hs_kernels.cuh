@@ -1527,6 +1527,16 @@ __device__ __forceinline__ unsigned hs_lds_u32(unsigned addr) {
 __device__ __forceinline__ void hs_reds_or(unsigned addr, unsigned v) {
   asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
+// explicit global-space stores (for pointers that were made opaque to the compiler, which would otherwise use generic stores)
+__device__ __forceinline__ void hs_stg(int* p, int v) { asm volatile("st.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void hs_stg_v4(int* p, int4 v) {
+  asm volatile("st.global.v4.s32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 hs_lds_f4(unsigned addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ unsigned hs_atoms_or(unsigned addr, unsigned v) {
   unsigned old;
   asm volatile("atom.shared.or.b32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
@@ -1595,6 +1605,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_raycast(HsParams P, int n
   unsigned short* tlo = reinterpret_cast<unsigned short*>(beams + P.max_points);   // per owner: first step inside the current band
   unsigned short* tlen = tlo + P.max_points;                                        // ... and the number of steps inside it
   __shared__ int s_box[4];  // xmin, ymin, xmax, ymax over the start cell and all valid end cells
+  __shared__ float4 s_addlut[16];   // sweep: the four addends of a quad by its 4 map bits
   __shared__ unsigned long long s_alloc;   // walk-list allocator: owners << 32 | segments (single band)
   __shared__ int s_items;
   __shared__ int s_wsum[32];
@@ -1684,6 +1695,10 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_raycast(HsParams P, int n
     for (int i = threadIdx.x; i < MAP_BYTES / 16; i += T) m4[i] = make_uint4(0u, 0u, 0u, 0u);
   }
   if (threadIdx.x == 0) { s_box[0] = INT_MAX; s_box[1] = INT_MAX; s_box[2] = INT_MIN; s_box[3] = INT_MIN; s_alloc = 0ULL; s_visits = 0u; }
+  if (threadIdx.x < 16) {
+    const unsigned b = threadIdx.x;
+    s_addlut[b] = make_float4((b & 1u) ? f : -0.0f, (b & 2u) ? f : -0.0f, (b & 4u) ? f : -0.0f, (b & 8u) ? f : -0.0f);
+  }
   __syncthreads();
 
   // phases A1 + A2: one thread per beam -- beam record, bounding box, and end point ownership (io = smallest beam index
@@ -1951,6 +1966,12 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_raycast(HsParams P, int n
       const int qpr = ((x1 - x0) >> 2) + 1;     // quads per box row (x0 is 32-aligned, W a multiple of 4)
       const int nq = qpr * rows;
       const int4 mf4 = make_int4(mark_free, mark_free, mark_free, mark_free);
+      const unsigned addlut_s = hs_shared_addr(s_addlut);
+      // the two plane pointers are made opaque here: the compiler otherwise re-derives each of them from the kernel parameters
+      // in front of every access (9 instructions per non-empty quad iteration)
+      float* valq = val;
+      int* idxq = idx;
+      asm volatile("" : "+l"(valq), "+l"(idxq));
       // a thread's quads are T apart in the row-major list; its position advances incrementally: c = quad in the row,
       // ni = nibble index into the cell map (row pitch pw*4 nibbles), gq = cell offset of the quad in the grid
       const int d_ry = T / qpr, d_c = T - d_ry * qpr;   // one stride of T quads, as (rows, quads)
@@ -1966,16 +1987,17 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_raycast(HsParams P, int n
           // val += f on the marked cells of the quad as ONE 16-byte floating-point reduction performed in L2 (IEEE round to
           // nearest, like the FADD of updateSetFree; nothing is loaded into or written back from registers). Unmarked cells
           // get -0.0f added, which leaves every value -- including +-0.0 -- bit for bit as it was.
-          const float a0 = (bits & 1u) ? f : -0.0f, a1 = (bits & 2u) ? f : -0.0f, a2 = (bits & 4u) ? f : -0.0f, a3 = (bits & 8u) ? f : -0.0f;
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(val + gq), "f"(a0), "f"(a1), "f"(a2), "f"(a3) : "memory");
+          const float4 a = hs_lds_f4(addlut_s + (bits << 4));   // (bit i ? f : -0.0f) for the quad's four cells: one 16-byte shared load instead of 8 selects
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(valq + gq), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w) : "memory");
           if (HS_DBG(P, 8)) {   // timing experiment (wrong markers): no free-marker stores
           } else if (bits == 0xFu || HS_DBG(P, 64)) {   // bit 6, timing experiment (wrong markers): every quad as one 16-byte store
-            *reinterpret_cast<int4*>(idx + gq) = mf4;
+            hs_stg_v4(idxq + gq, mf4);
           } else {
-            if (bits & 1u) idx[gq] = mark_free;
-            if (bits & 2u) idx[gq + 1] = mark_free;
-            if (bits & 4u) idx[gq + 2] = mark_free;
-            if (bits & 8u) idx[gq + 3] = mark_free;
+            int* iq = idxq + gq;
+            if (bits & 1u) hs_stg(iq, mark_free);
+            if (bits & 2u) hs_stg(iq + 1, mark_free);
+            if (bits & 4u) hs_stg(iq + 2, mark_free);
+            if (bits & 8u) hs_stg(iq + 3, mark_free);
           }
         }
         c += d_c; ni += ni_step; gq += gq_step;

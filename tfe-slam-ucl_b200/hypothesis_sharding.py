@@ -55,10 +55,13 @@ def bench_record(hs, torch, dist, local_rank, rank, world, n_hyp=4096, reps=20):
     sc = workload.scene_preset(workload.SCENE_RPLIDAR_ROOM)
     ranges, _ = workload.scangen_batch(sc, 0xC0FFEE, 1, 0, 201, truth=False)
     pts, cnt = workload.scan_to_points_host(ranges, sc, 20.0)
-    with hs.Engine(n_streams=1, max_points=360, device=local_rank) as eng:
+    # one explicit CUDA stream for the engine's kernels, the collectives (torch issues them behind the CURRENT stream) and the
+    # timing events -- the legacy default stream's handle is 0, which hs_set_cuda_stream reads as "use the engine's own stream"
+    side = torch.cuda.Stream(device=dev)
+    with hs.Engine(n_streams=1, max_points=360, device=local_rank) as eng, torch.cuda.stream(side):
         eng.set_update_factor_free(0.4); eng.set_update_factor_occupied(0.9)
         eng.set_map_update_min_dist_diff(0.0); eng.set_map_update_min_angle_diff(0.0)
-        eng.set_cuda_stream(torch.cuda.current_stream().cuda_stream)
+        eng.set_cuda_stream(side.cuda_stream)
         pose = np.zeros((1, 3), np.float32)
         if rank == 0:
             for k in range(200):
@@ -82,20 +85,20 @@ def bench_record(hs, torch, dist, local_rank, rank, world, n_hyp=4096, reps=20):
             evaluate_sharded(eng, torch, dist, rank, world, 0, d_pose, n_hyp, d_pts, p.shape[0], d_H, d_d)
         torch.cuda.synchronize(); dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        e0.record(side)
         for _ in range(reps):
             evaluate_sharded(eng, torch, dist, rank, world, 0, d_pose, n_hyp, d_pts, p.shape[0], d_H, d_d)
-        e1.record()
+        e1.record(side)
         torch.cuda.synchronize()
         _, t_sharded = sharding.aggregate_throughput(0, e0.elapsed_time(e1) * 1e-3 / reps, device=dev)
         H_sh, d_sh = d_H.cpu().numpy(), d_d.cpu().numpy()
         # the same on rank 0 alone
         d_H1 = torch.zeros((n_hyp, 9), device=dev); d_d1 = torch.zeros((n_hyp, 3), device=dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        e0.record(side)
         for _ in range(reps):
             eng.hessian_derivs_batch_device(0, 0, d_pose.data_ptr(), n_hyp, d_pts.data_ptr(), p.shape[0], d_H1.data_ptr(), d_d1.data_ptr())
-        e1.record()
+        e1.record(side)
         torch.cuda.synchronize()
         t_single = e0.elapsed_time(e1) * 1e-3 / reps
         same = bool(np.array_equal(H_sh.view(np.int32), d_H1.cpu().numpy().view(np.int32)) and
