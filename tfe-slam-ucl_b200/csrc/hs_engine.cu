@@ -322,6 +322,8 @@ int hs_create(const hs_config* cfg, hs_engine** out) {
   }
   HS_ALLOC(P.val, cells * sizeof(float));
   HS_ALLOC(P.idx, cells * sizeof(int));
+  HS_ALLOC(P.mk, cells * sizeof(uint8_t));
+  HS_ALLOC(P.mk_base, ns * HS_MAX_LEVELS * sizeof(int));
   HS_ALLOC(P.last_pose, ns * 3 * sizeof(float));
   HS_ALLOC(P.last_update_pose, ns * 3 * sizeof(float));
   HS_ALLOC(P.cov, ns * 9 * sizeof(float));
@@ -427,7 +429,7 @@ int hs_create(const hs_config* cfg, hs_engine** out) {
   cudaMemsetAsync(P.coarse_pts, 0, ns * mp * 2 * sizeof(float), e->stream);
   k_reset_state<<<(cfg->n_streams + 127) / 128, 128, 0, e->stream>>>(P, 0, cfg->n_streams, 1);
   e->launches++;
-  k_clear_cells<<<148 * 8, 256, 0, e->stream>>>(P.val, P.idx, cells);
+  k_clear_cells<<<148 * 8, 256, 0, e->stream>>>(P.val, P.idx, P.mk, cells);
   e->launches++;
   cudaError_t err = cudaStreamSynchronize(e->stream);
   if (err != cudaSuccess) {
@@ -454,7 +456,7 @@ int hs_destroy(hs_engine* e) {
     cudaFree(e->P.dbg_times);
   }
   HsParams& P = e->P;
-  void* ptrs[] = {P.val, P.idx, P.last_pose, P.last_update_pose, P.cov, P.cur_update_index, P.last_update_index,
+  void* ptrs[] = {P.val, P.idx, P.mk, P.mk_base, P.last_pose, P.last_update_pose, P.cov, P.cur_update_index, P.last_update_index,
                   P.coarse_pts, P.coarse_cnt, P.coarse_origo, P.slot_pose, P.slot_sc, P.slot_integrate, P.slot_mark_base, P.counters,
                   e->d_points, e->d_counts, e->d_origos, e->d_hints, e->d_flags, e->d_ids, e->d_ranges, e->d_out,
                   e->d_beam_cs, e->d_scratch, e->pblk};
@@ -496,7 +498,7 @@ int hs_reset(hs_engine* e, int stream) {
   HS_LAUNCHED(e);
   size_t cells = (size_t)n * (size_t)e->P.cells_per_stream;
   size_t base = (size_t)first * (size_t)e->P.cells_per_stream;
-  k_clear_cells<<<148 * 8, 256, 0, e->stream>>>(e->P.val + base, e->P.idx + base, cells);
+  k_clear_cells<<<148 * 8, 256, 0, e->stream>>>(e->P.val + base, e->P.idx + base, e->P.mk + base, cells);
   HS_LAUNCHED(e);
   return HS_OK;
 }
@@ -1499,7 +1501,8 @@ int hs_download_level(hs_engine* e, int stream, int level, hs_cell* cells_out) {
   size_t n = (size_t)L.sx * L.sy;
   if ((st = ensure_scratch(e, n * sizeof(hs_cell))) != HS_OK) return st;
   size_t base = (size_t)stream * (size_t)e->P.cells_per_stream + (size_t)L.cell_offset;
-  k_pack_cells<<<148 * 4, 256, 0, e->stream>>>(e->P.val + base, e->P.idx + base, (hs_cell*)e->d_scratch, n);
+  k_pack_cells<<<148 * 4, 256, 0, e->stream>>>(e->P.val + base, e->P.idx + base, e->P.mk + base,
+                                               e->P.mk_base + (size_t)stream * HS_MAX_LEVELS + level, (hs_cell*)e->d_scratch, n);
   HS_LAUNCHED(e);
   HS_CK(cudaMemcpyAsync(cells_out, e->d_scratch, n * sizeof(hs_cell), cudaMemcpyDeviceToHost, e->stream));
   e->d2h_bytes += n * sizeof(hs_cell);
@@ -1519,7 +1522,7 @@ int hs_upload_level(hs_engine* e, int stream, int level, const hs_cell* cells_in
   e->map_epoch++;
   HS_CK(cudaMemcpyAsync(e->d_scratch, cells_in, n * sizeof(hs_cell), cudaMemcpyHostToDevice, e->stream));
   e->h2d_bytes += n * sizeof(hs_cell);
-  k_unpack_cells<<<148 * 4, 256, 0, e->stream>>>((const hs_cell*)e->d_scratch, e->P.val + base, e->P.idx + base, n);
+  k_unpack_cells<<<148 * 4, 256, 0, e->stream>>>((const hs_cell*)e->d_scratch, e->P.val + base, e->P.idx + base, e->P.mk + base, n);
   HS_LAUNCHED(e);
   HS_CK(cudaStreamSynchronize(e->stream));
   return HS_OK;
@@ -1590,6 +1593,8 @@ int hs_copy_stream_maps(hs_engine* dst, int dst_stream, hs_engine* src, int src_
   if (dst == src && dst_stream == src_stream) return HS_OK;
   const size_t cells = (size_t)src->P.cells_per_stream;
   HS_CK(cudaSetDevice(src->device));
+  k_fold_markers<<<src->P.n_levels, 512, 0, src->stream>>>(src->P, src_stream);   // the int32 marker plane is complete afterwards
+  HS_LAUNCHED(src);
   HS_CK(cudaStreamSynchronize(src->stream));       // the source maps are final
   HS_CK(cudaSetDevice(dst->device));
   dst->map_epoch++;
@@ -1597,6 +1602,7 @@ int hs_copy_stream_maps(hs_engine* dst, int dst_stream, hs_engine* src, int src_
                             cells * sizeof(float), dst->stream));
   HS_CK(cudaMemcpyPeerAsync(dst->P.idx + (size_t)dst_stream * cells, dst->device, src->P.idx + (size_t)src_stream * cells, src->device,
                             cells * sizeof(int), dst->stream));
+  HS_CK(cudaMemsetAsync(dst->P.mk + (size_t)dst_stream * cells, 0, cells, dst->stream));
   HS_CK(cudaStreamSynchronize(dst->stream));
   return HS_OK;
 }

@@ -6,7 +6,13 @@
 //
 // Data layout in HBM (per engine):
 //   val[stream][level-concatenated cells]  float   log-odds  (LogOddsCell::logOddsVal)
-//   idx[stream][level-concatenated cells]  int32   update marker (LogOddsCell::updateIndex)
+//   idx[stream][level-concatenated cells]  int32   update marker (LogOddsCell::updateIndex), cold plane
+//   mk [stream][level-concatenated cells]  uint8   update marker, hot plane: what the ray-caster writes. A scan marks ~26 k
+//        cells, most of them in partly marked 32-byte sectors whose write makes HBM read the sector first; with one byte per
+//        cell a sector holds 32 cells instead of 8. b != 0: updateIndex = mk_base[stream][level] + b (markers grow by 3 per
+//        integrated scan, so a base lasts 84 scans); b == 0: the int32 plane holds the marker. When the next scan's markers
+//        would not fit a byte, the (stream, level)'s ray-cast CTA first folds the byte plane into the int32 plane and
+//        re-bases (hs_fold_markers). Readers (k_pack_cells) merge the two planes.
 // i.e. the reference's AoS {float,int} cell split into two planes: the matcher gathers touch only
 // `val` (8 cells per 32 B sector instead of 4), the ray-caster's "already marked this scan?" test touches
 // only `idx`. Levels of one stream are contiguous; rows are row-major cell[y*W + x] as in
@@ -72,7 +78,9 @@ struct HsParams {
   float min_dist, min_angle;          // paramMinDistanceDiffForMapUpdate / AngleDiff (HectorSlamProcessor.h:138-139)
   // grids
   float* val;
-  int* idx;
+  int* idx;                  // update markers, int32 plane: authoritative where the byte plane holds 0
+  uint8_t* mk;               // update markers, hot byte plane: b != 0 means updateIndex = mk_base[stream][level] + b
+  int* mk_base;              // [n_streams][HS_MAX_LEVELS]
   // per-stream state
   float* last_pose;          // [n_streams][3] lastScanMatchPose
   float* last_update_pose;   // [n_streams][3] lastMapUpdatePose
@@ -1528,10 +1536,8 @@ __device__ __forceinline__ void hs_reds_or(unsigned addr, unsigned v) {
   asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 // explicit global-space stores (for pointers that were made opaque to the compiler, which would otherwise use generic stores)
-__device__ __forceinline__ void hs_stg(int* p, int v) { asm volatile("st.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-__device__ __forceinline__ void hs_stg_v4(int* p, int4 v) {
-  asm volatile("st.global.v4.s32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
+__device__ __forceinline__ void hs_stg_u8(uint8_t* p, unsigned v) { asm volatile("st.global.u8 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void hs_stg_u32(uint8_t* p, unsigned v) { asm volatile("st.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ float4 hs_lds_f4(unsigned addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
@@ -1583,6 +1589,48 @@ __device__ __forceinline__ void hs_free_hits_end_cell(const int* __restrict__ hk
     int hv = hvals[h];
     if (beam < (hv >> 1) && !(hv & 1)) atomicOr(&hvals[h], 1);
   }
+}
+
+// Folds the byte marker plane of n cells into the int32 plane (b != 0: idx = base + b; b = 0) -- all threads of the CTA.
+// 16 cells per 16-byte load where the slab is aligned; almost every word is zero except around the robot.
+__device__ __forceinline__ void hs_fold_markers(uint8_t* __restrict__ mk, int* __restrict__ idx, size_t n, int base, int tid, int T) {
+  if ((reinterpret_cast<uintptr_t>(mk) & 15) == 0) {
+    uint4* m4 = reinterpret_cast<uint4*>(mk);
+    const size_t n16 = n >> 4;
+    for (size_t i = tid; i < n16; i += T) {
+      const uint4 w = m4[i];
+      if (w.x | w.y | w.z | w.w) {
+        const unsigned ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            const unsigned v = (ww[q] >> (8 * b)) & 0xFFu;
+            if (v) idx[(i << 4) + q * 4 + b] = base + (int)v;
+          }
+        m4[i] = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+    for (size_t i = (n16 << 4) + tid; i < n; i += T) {
+      const unsigned v = mk[i];
+      if (v) { idx[i] = base + (int)v; mk[i] = 0; }
+    }
+  } else {
+    for (size_t i = tid; i < n; i += T) {
+      const unsigned v = mk[i];
+      if (v) { idx[i] = base + (int)v; mk[i] = 0; }
+    }
+  }
+}
+
+// k_fold_markers: the same for every level of one stream (before the int32 plane is copied or handed out as it is).
+// One CTA per level; the bases stay as they are (with all bytes zero they mean nothing).
+__global__ void __launch_bounds__(512) k_fold_markers(HsParams P, int stream) {
+  const int level = blockIdx.x;
+  if (level >= P.n_levels) return;
+  const HsLevel& L = P.lv[level];
+  const size_t off = (size_t)stream * P.cells_per_stream + L.cell_offset;
+  hs_fold_markers(P.mk + off, P.idx + off, (size_t)L.sx * L.sy, P.mk_base[(size_t)stream * HS_MAX_LEVELS + level], threadIdx.x, blockDim.x);
 }
 
 // dynamic shared memory: HS_MAP_BYTES (cell map) | hash keys[T] | hash vals[T] | max_points * sizeof(HsWalkRec)
@@ -1645,6 +1693,8 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_raycast(HsParams P, int n
   const int s_map = HS_DBG(P, 256) ? (s & 7) : s;   // timing experiment (wrong results): all CTAs share 8 streams' grids, which fit in L2
   float* val = P.val + (size_t)s_map * P.cells_per_stream + L.cell_offset;
   int* idx = P.idx + (size_t)s_map * P.cells_per_stream + L.cell_offset;
+  uint8_t* mk = P.mk + (size_t)s_map * P.cells_per_stream + L.cell_offset;
+  const int mk_base_old = P.mk_base[(size_t)s * HS_MAX_LEVELS + level];
   const int W = L.sx;
   constexpr int T = THREADS;   // == blockDim.x: divisions and strides by T compile to multiplications / immediates
 
@@ -1672,6 +1722,16 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_raycast(HsParams P, int n
   n = n < 0 ? 0 : (n > P.max_points ? P.max_points : n);
   const int mark_free = mark_base + 1, mark_occ = mark_base + 2;
   const float f = P.log_odds_free, o = P.log_odds_occ;
+  // markers of this scan as bytes relative to the (stream, level)'s base; if they do not fit (every 84 integrated scans, or
+  // after the counters were set from outside), fold the byte plane into the int32 plane first and start a new base
+  int mk_base = mk_base_old;
+  if ((unsigned)(mark_free - mk_base - 1) > 253u) {   // CTA-uniform
+    hs_fold_markers(mk, idx, (size_t)L.sx * L.sy, mk_base_old, threadIdx.x, THREADS);
+    mk_base = mark_base;
+    __syncthreads();
+    if (threadIdx.x == 0) P.mk_base[(size_t)s * HS_MAX_LEVELS + level] = mk_base;
+  }
+  const unsigned b_free = (unsigned)(mark_free - mk_base), b_occ = (unsigned)(mark_occ - mk_base);   // 1 .. 255
 
   float mpx, mpy;
   hs_world_to_map(L, pose_x, pose_y, mpx, mpy);
@@ -1965,13 +2025,13 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_raycast(HsParams P, int n
       // thread. Unmarked components are written back unchanged, hence the barrier before phase C touches the end cells.
       const int qpr = ((x1 - x0) >> 2) + 1;     // quads per box row (x0 is 32-aligned, W a multiple of 4)
       const int nq = qpr * rows;
-      const int4 mf4 = make_int4(mark_free, mark_free, mark_free, mark_free);
       const unsigned addlut_s = hs_shared_addr(s_addlut);
       // the two plane pointers are made opaque here: the compiler otherwise re-derives each of them from the kernel parameters
       // in front of every access (9 instructions per non-empty quad iteration)
       float* valq = val;
-      int* idxq = idx;
-      asm volatile("" : "+l"(valq), "+l"(idxq));
+      uint8_t* mkq = mk;
+      asm volatile("" : "+l"(valq), "+l"(mkq));
+      const unsigned bf4 = b_free * 0x01010101u;
       // a thread's quads are T apart in the row-major list; its position advances incrementally: c = quad in the row,
       // ni = nibble index into the cell map (row pitch pw*4 nibbles), gq = cell offset of the quad in the grid
       const int d_ry = T / qpr, d_c = T - d_ry * qpr;   // one stride of T quads, as (rows, quads)
@@ -1990,14 +2050,14 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_raycast(HsParams P, int n
           const float4 a = hs_lds_f4(addlut_s + (bits << 4));   // (bit i ? f : -0.0f) for the quad's four cells: one 16-byte shared load instead of 8 selects
           asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(valq + gq), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w) : "memory");
           if (HS_DBG(P, 8)) {   // timing experiment (wrong markers): no free-marker stores
-          } else if (bits == 0xFu || HS_DBG(P, 64)) {   // bit 6, timing experiment (wrong markers): every quad as one 16-byte store
-            hs_stg_v4(idxq + gq, mf4);
+          } else if (bits == 0xFu || HS_DBG(P, 64)) {   // bit 6, timing experiment (wrong markers): every quad as one store
+            hs_stg_u32(mkq + gq, bf4);
           } else {
-            int* iq = idxq + gq;
-            if (bits & 1u) hs_stg(iq, mark_free);
-            if (bits & 2u) hs_stg(iq + 1, mark_free);
-            if (bits & 4u) hs_stg(iq + 2, mark_free);
-            if (bits & 8u) hs_stg(iq + 3, mark_free);
+            uint8_t* mq = mkq + gq;
+            if (bits & 1u) hs_stg_u8(mq, b_free);
+            if (bits & 2u) hs_stg_u8(mq + 1, b_free);
+            if (bits & 4u) hs_stg_u8(mq + 2, b_free);
+            if (bits & 8u) hs_stg_u8(mq + 3, b_free);
           }
         }
         c += d_c; ni += ni_step; gq += gq_step;
@@ -2014,7 +2074,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_raycast(HsParams P, int n
           const bool on = (x0 + (sg << 5) + lane <= x1) && (((mw & ~(mw >> 16)) >> (lane & 15)) & 1u);   // free and not an end cell
           if (on) {
             val[row + (sg << 5)] = val[row + (sg << 5)] + f;
-            idx[row + (sg << 5)] = mark_free;
+            mk[row + (sg << 5)] = (uint8_t)b_free;
           }
         }
       }
@@ -2037,7 +2097,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_raycast(HsParams P, int n
     if (hv & 1) v = (v + f) - f;       // updateSetFree by an earlier beam, then updateUnsetFree
     if (v < 50.0f) v = v + o;          // updateSetOccupied
     val[r.kend] = v;
-    idx[r.kend] = mark_occ;
+    mk[r.kend] = (uint8_t)b_occ;
   }
 #ifdef HS_EXPERIMENTS
   if (P.dbg_times) { __syncthreads(); hs_stamp(P, 5); }
@@ -2048,10 +2108,10 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_raycast(HsParams P, int n
 // maintenance kernels
 
 // GridMapBase::clear -> LogOddsCell::resetGridCell (GridMapBase.h:69-87, GridMapLogOdds.h:89-93)
-__global__ void k_clear_cells(float* __restrict__ val, int* __restrict__ idx, size_t n) {
+__global__ void k_clear_cells(float* __restrict__ val, int* __restrict__ idx, uint8_t* __restrict__ mk, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) { val[i] = 0.0f; idx[i] = -1; }
+  for (; i < n; i += stride) { val[i] = 0.0f; idx[i] = -1; mk[i] = 0; }
 }
 
 // HectorSlamProcessor::reset state (HectorSlamProcessor.h:115-124); update counters keep counting.
@@ -2064,21 +2124,31 @@ __global__ void k_reset_state(HsParams P, int first, int n, int init_counters) {
     for (int k = 0; k < 9; ++k) P.cov[9 * s + k] = 0.0f;
     P.cur_update_index[s] = 0;
     P.last_update_index[s] = -1;
+    for (int l = 0; l < HS_MAX_LEVELS; ++l) P.mk_base[(size_t)s * HS_MAX_LEVELS + l] = 0;
     P.coarse_cnt[s] = 0;
     P.coarse_origo[2 * s] = 0.0f; P.coarse_origo[2 * s + 1] = 0.0f;
   }
 }
 
 // interleave / de-interleave one level between the SoA planes and the reference's {float,int} cells
-__global__ void k_pack_cells(const float* __restrict__ val, const int* __restrict__ idx, hs_cell* __restrict__ out, size_t n) {
+// (the marker is the byte plane's where that holds one, the int32 plane's otherwise)
+__global__ void k_pack_cells(const float* __restrict__ val, const int* __restrict__ idx, const uint8_t* __restrict__ mk,
+                             const int* __restrict__ mk_base, hs_cell* __restrict__ out, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) { hs_cell c; c.logOddsVal = val[i]; c.updateIndex = idx[i]; out[i] = c; }
+  const int base = *mk_base;
+  for (; i < n; i += stride) {
+    hs_cell c;
+    const unsigned b = mk[i];
+    c.logOddsVal = val[i];
+    c.updateIndex = b ? base + (int)b : idx[i];
+    out[i] = c;
+  }
 }
-__global__ void k_unpack_cells(const hs_cell* __restrict__ in, float* __restrict__ val, int* __restrict__ idx, size_t n) {
+__global__ void k_unpack_cells(const hs_cell* __restrict__ in, float* __restrict__ val, int* __restrict__ idx, uint8_t* __restrict__ mk, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) { hs_cell c = in[i]; val[i] = c.logOddsVal; idx[i] = c.updateIndex; }
+  for (; i < n; i += stride) { hs_cell c = in[i]; val[i] = c.logOddsVal; idx[i] = c.updateIndex; mk[i] = 0; }
 }
 // HectorMappingRos::publishMap classification (HectorMappingRos.cpp:447-470): isFree -> 0, isOccupied -> 100, else -1
 __global__ void k_classify(const float* __restrict__ val, int8_t* __restrict__ out, size_t n) {
