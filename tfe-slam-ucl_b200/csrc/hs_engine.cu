@@ -142,7 +142,7 @@ static int launch_raycast(hs_engine* e, const HsParams& Pc, int n, const int32_t
 #ifdef HS_EXPERIMENTS
   if (const char* ol = getenv("HSGPU_DEBUG_ONLY_LEVEL")) {   // timing experiment (wrong maps): one level's CTAs alone
     const int l = atoi(ol);
-    k_raycast<HS_RAYCAST_THREADS, HS_MAP_BYTES, 3><<<n, HS_RAYCAST_THREADS, raycast_smem_for(e->P.max_points), st>>>(
+    k_raycast<HS_RAYCAST_THREADS, HS_MAP_BYTES, HS_RAYCAST_CTAS><<<n, HS_RAYCAST_THREADS, raycast_smem_for(e->P.max_points), st>>>(
         Pc, n, ids, points, counts, origos, log2_hash, e->log2_seg_levels, l, 1);
     return hs_launch_check(e);
   }
@@ -151,7 +151,7 @@ static int launch_raycast(hs_engine* e, const HsParams& Pc, int n, const int32_t
     k_raycast<HS_RAYCAST_THREADS_BIG, HS_MAP_BYTES_BIG, 1><<<n * e->P.n_levels, HS_RAYCAST_THREADS_BIG, raycast_smem_for(e->P.max_points, HS_MAP_BYTES_BIG), st>>>(
         Pc, n, ids, points, counts, origos, log2_hash, e->log2_seg_levels, 0, e->P.n_levels);
   else
-    k_raycast<HS_RAYCAST_THREADS, HS_MAP_BYTES, 3><<<n * e->P.n_levels, HS_RAYCAST_THREADS, raycast_smem_for(e->P.max_points), st>>>(
+    k_raycast<HS_RAYCAST_THREADS, HS_MAP_BYTES, HS_RAYCAST_CTAS><<<n * e->P.n_levels, HS_RAYCAST_THREADS, raycast_smem_for(e->P.max_points), st>>>(
         Pc, n, ids, points, counts, origos, log2_hash, e->log2_seg_levels, 0, e->P.n_levels);
   return hs_launch_check(e);
 }
@@ -405,9 +405,9 @@ int hs_create(const hs_config* cfg, hs_engine** out) {
     }
     if (const char* mt = getenv("HSGPU_MATCH2_THREADS")) e->match2_threads = atoi(mt);
     int smem_r = (int)raycast_smem_for(cfg->max_points);  // k_raycast's cell map + hash table + beam records
-    cudaError_t e3 = cudaFuncSetAttribute(k_raycast<HS_RAYCAST_THREADS, HS_MAP_BYTES, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_r);
-    // one CTA per SM anyway (more than half of the SM's shared memory per CTA): use the big-CTA instantiation if it fits
-    e->ray_big = (size_t)smem_r * 2 > (size_t)optin_smem && raycast_smem_for(cfg->max_points, HS_MAP_BYTES_BIG) <= (size_t)optin_smem;
+    cudaError_t e3 = cudaFuncSetAttribute(k_raycast<HS_RAYCAST_THREADS, HS_MAP_BYTES, HS_RAYCAST_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_r);
+    // long scans: ~80 KB of tables per CTA leave room for one or two CTAs per SM only -- use the big-CTA instantiation if it fits
+    e->ray_big = cfg->max_points > 768 && raycast_smem_for(cfg->max_points, HS_MAP_BYTES_BIG) <= (size_t)optin_smem;
     if (const char* sp = getenv("HSGPU_RAYCAST_BIG")) e->ray_big = atoi(sp) != 0 && raycast_smem_for(cfg->max_points, HS_MAP_BYTES_BIG) <= (size_t)optin_smem;
     if (e3 == cudaSuccess && e->ray_big)
       e3 = cudaFuncSetAttribute(k_raycast<HS_RAYCAST_THREADS_BIG, HS_MAP_BYTES_BIG, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -1466,9 +1466,15 @@ __global__ void __launch_bounds__(128) k_occupancy_ray(HsParams P, int stream, i
 // abs_da cells from the start).
 
 #define HS_HASH_EMPTY (-1)
-#define HS_MAP_BYTES 49152                 // shared-memory cell map: 2 bits per cell, 16 cells per 32-bit word
-                                           // (low half-word: crossed by a free trace; high half-word: some beam's end cell)
+#ifndef HS_MAP_BYTES
+#define HS_MAP_BYTES 32768                 // shared-memory cell map: 2 bits per cell, 16 cells per 32-bit word
+#endif                                     // (low half-word: crossed by a free trace; high half-word: some beam's end cell)
+#ifndef HS_RAYCAST_THREADS
 #define HS_RAYCAST_THREADS 384
+#endif
+#ifndef HS_RAYCAST_CTAS
+#define HS_RAYCAST_CTAS 4                  // CTAs per SM the default instantiation is compiled for (register cap 65536 / (CTAS * THREADS))
+#endif
 // long scans (hash table + beam records of ~80 KB: one CTA per SM anyway): the CTA takes the whole SM
 #define HS_MAP_BYTES_BIG 147456
 #define HS_RAYCAST_THREADS_BIG 1024
