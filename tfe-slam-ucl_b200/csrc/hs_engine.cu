@@ -305,18 +305,6 @@ int hs_create(const hs_config* cfg, hs_engine** out) {
     s1 = s1 < 0 ? 0 : (s1 > 12 ? 12 : s1);
     e->log2_seg_levels = s0 | (s1 << 8);
   }
-  {   // 32-bit walk-list allocator (owners << bits | segments): a trace has at most max(sx, sy) cells, so the segment count of a
-      // scan is bounded by max_points * ceil(max_dim / segment length); use it when both fields fit
-    int owner_bits = 1;
-    while ((1 << owner_bits) <= cfg->max_points) ++owner_bits;
-    const int seg_bits = 32 - owner_bits;
-    const int s0 = e->log2_seg_levels & 0xFF, s1 = e->log2_seg_levels >> 8;
-    const long long dim0 = cfg->map_size_x > cfg->map_size_y ? cfg->map_size_x : cfg->map_size_y;
-    const long long per_beam0 = (dim0 + (1 << s0) - 1) >> s0, per_beam1 = ((dim0 / 2) + (1 << s1) - 1) >> s1;
-    const long long worst = (long long)cfg->max_points * (per_beam0 > per_beam1 ? per_beam0 : per_beam1);
-    P.alloc_seg_bits = worst < (1LL << seg_bits) ? seg_bits : 0;
-    if (const char* a = getenv("HSGPU_RAYCAST_ALLOC32")) { if (!atoi(a)) P.alloc_seg_bits = 0; }
-  }
   e->free_factor = 0.4f;
   e->occ_factor = 0.6f;
   P.log_odds_free = prob_to_log_odds(0.4f);

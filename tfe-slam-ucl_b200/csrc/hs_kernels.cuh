@@ -67,7 +67,6 @@ struct HsParams {
   int serial_spread;                // k_match: 1 = the serial warps of the CTAs sharing an SM use two sub-partitions instead of one
   int reverse_order;                // k_raycast: this launch walks the slots from the last to the first
   int l2_keep_levels;               // bit l: the matcher's gathers on level l carry an L2 evict-last hint
-  int alloc_seg_bits;               // k_raycast: width of the segment field of the 32-bit walk-list allocator, 0 = use the 64-bit one
   int tail_slots;                   // k_raycast: the last `tail_slots` slots of a launch are dispatched level-major
   int slot0;                        // first slot of this launch (a host batch may be cut into chunks that run on several CUDA streams)
   int dbg_skip;                     // timing experiments only (HSGPU_DEBUG_SKIP): bit0 skip walk, bit1 skip sweep, bit2 skip end points
@@ -1662,8 +1661,6 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_raycast(HsParams P, int n
   __shared__ int s_box[4];  // xmin, ymin, xmax, ymax over the start cell and all valid end cells
   __shared__ float4 s_addlut[16];   // sweep: the four addends of a quad by its 4 map bits
   __shared__ unsigned long long s_alloc;   // walk-list allocator: owners << 32 | segments (single band)
-  __shared__ unsigned s_alloc32;           // the same packed into 32 bits (owners << P.alloc_seg_bits | segments) when the host found that
-                                           // it fits: a 64-bit shared-memory atomicAdd is a compare-and-swap loop (ATOMS.CAST.SPIN)
   __shared__ int s_items;
   __shared__ int s_wsum[32];
   __shared__ unsigned s_visits;
@@ -1763,7 +1760,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_raycast(HsParams P, int n
     uint4* m4 = reinterpret_cast<uint4*>(hs_smem);
     for (int i = threadIdx.x; i < MAP_BYTES / 16; i += T) m4[i] = make_uint4(0u, 0u, 0u, 0u);
   }
-  if (threadIdx.x == 0) { s_box[0] = INT_MAX; s_box[1] = INT_MAX; s_box[2] = INT_MIN; s_box[3] = INT_MIN; s_alloc = 0ULL; s_alloc32 = 0u; s_visits = 0u; }
+  if (threadIdx.x == 0) { s_box[0] = INT_MAX; s_box[1] = INT_MAX; s_box[2] = INT_MIN; s_box[3] = INT_MIN; s_alloc = 0ULL; s_visits = 0u; }
   if (threadIdx.x < 16) {
     const unsigned b = threadIdx.x;
     s_addlut[b] = make_float4((b & 1u) ? f : -0.0f, (b & 2u) ? f : -0.0f, (b & 4u) ? f : -0.0f, (b & 8u) ? f : -0.0f);
@@ -1851,15 +1848,8 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_raycast(HsParams P, int n
     }
     const unsigned m = __ballot_sync(0xffffffffu, owner);
     unsigned long long base = 0ULL;
-    if (P.alloc_seg_bits) {
-      unsigned b32 = 0u;
-      if (lane == 31 && m) b32 = atomicAdd(&s_alloc32, ((unsigned)__popc(m) << P.alloc_seg_bits) | (unsigned)incl);
-      b32 = __shfl_sync(0xffffffffu, b32, 31);
-      base = ((unsigned long long)(b32 >> P.alloc_seg_bits) << 32) | (unsigned long long)(b32 & ((1u << P.alloc_seg_bits) - 1u));
-    } else {
-      if (lane == 31 && m) base = atomicAdd(&s_alloc, ((unsigned long long)__popc(m) << 32) | (unsigned long long)(unsigned)incl);
-      base = __shfl_sync(0xffffffffu, base, 31);
-    }
+    if (lane == 31 && m) base = atomicAdd(&s_alloc, ((unsigned long long)__popc(m) << 32) | (unsigned long long)(unsigned)incl);
+    base = __shfl_sync(0xffffffffu, base, 31);
     if (owner) {
       const int sa = (r.flags & 2) ? 1 : -1, sb = (r.flags & 4) ? 1 : -1;
       const int off_a = (r.flags & 1) ? sa : sa * pitch;
@@ -1887,10 +1877,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_raycast(HsParams P, int n
     }
   }
   __syncthreads();
-  const unsigned long long alloc_total = P.alloc_seg_bits ? (((unsigned long long)(s_alloc32 >> P.alloc_seg_bits) << 32) |
-                                                              (unsigned long long)(s_alloc32 & ((1u << P.alloc_seg_bits) - 1u)))
-                                                           : s_alloc;
-  const int n_walk = (int)(alloc_total >> 32);
+  const int n_walk = (int)(s_alloc >> 32);
   hs_stamp(P, 2);
 
   const int warp = threadIdx.x >> 5, n_warps = T >> 5;
@@ -1963,7 +1950,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_raycast(HsParams P, int n
       if (threadIdx.x == T - 1) s_items = off + incl;
     }
     if (!SINGLE) __syncthreads();
-    const int n_items = SINGLE ? (int)(unsigned)(alloc_total & 0xFFFFFFFFULL) : s_items;
+    const int n_items = SINGLE ? (int)(unsigned)(s_alloc & 0xFFFFFFFFULL) : s_items;
 
     // phase B1: free cells with the reference's bresenham2D recurrence (OccGridMapBase.h:243-260). Every thread takes
     // the same number of consecutive walk segments (so the longest beam does not set the CTA's pace); a thread that
