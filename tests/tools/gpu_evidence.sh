@@ -1,5 +1,5 @@
 #!/bin/bash
-# final-ish evidence run: bench lines (both arms), launch list, ncu --set full captures of every hot kernel
+# evidence run (round 2): bench lines (both arms), launch list, ncu --set full captures of every hot kernel
 mkdir -p gpurun_out
 python bench.py --steps 20 --warmup 5 > gpurun_out/r02_bench_n1.json 2> gpurun_out/s9_bench.err; tail -c 300 gpurun_out/s9_bench.err
 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/r02_bench_reference_n1.json 2>> gpurun_out/s9_bench.err

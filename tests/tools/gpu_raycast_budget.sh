@@ -1,4 +1,7 @@
 #!/bin/bash
+# k_raycast time budget with the timing switches of the EXPERIMENTS build (results are wrong whenever a switch is set):
+#   make -C tfe-slam-ucl_b200/csrc OUT=$PWD/tmp_ab/libhsgpu_exp.so LOG=/tmp/x.log EXPERIMENTS=1    (before calling this)
+# HSGPU_DEBUG_SKIP bits: 1 no walk, 2 no sweep, 8 no free-marker stores; HSGPU_DEBUG_ONLY_LEVEL=l: one level's CTAs alone
 mkdir -p gpurun_out
 LIB=tfe-slam-ucl_b200/libhsgpu.so
 cp $LIB tmp_ab/libhsgpu__intree.so
