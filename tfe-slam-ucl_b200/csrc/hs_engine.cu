@@ -135,7 +135,6 @@ static size_t match2_smem_for(int max_points) {
 // SM: it then takes the whole SM -- 1024 threads and a 144 KB map (590 k cells per band instead of 197 k).
 // Measured and dropped on B200 (configs[1]): the coarse levels as a second, concurrent launch of 128-thread CTAs with a 12 KB
 // map (k_raycast 163 -> 182 us: the small CTAs are slower than the slots they free).
-static bool raycast_big(const hs_engine* e) { return e->ray_big; }
 static int launch_raycast(hs_engine* e, const HsParams& Pc, int n, const int32_t* ids, const float2* points, const int32_t* counts,
                           const float2* origos, cudaStream_t st) {
   const int log2_hash = raycast_log2_hash(e->P.max_points);
@@ -147,7 +146,7 @@ static int launch_raycast(hs_engine* e, const HsParams& Pc, int n, const int32_t
     return hs_launch_check(e);
   }
 #endif
-  if (raycast_big(e))
+  if (e->ray_big)
     k_raycast<HS_RAYCAST_THREADS_BIG, HS_MAP_BYTES_BIG, 1><<<n * e->P.n_levels, HS_RAYCAST_THREADS_BIG, raycast_smem_for(e->P.max_points, HS_MAP_BYTES_BIG), st>>>(
         Pc, n, ids, points, counts, origos, log2_hash, e->log2_seg_levels, 0, e->P.n_levels);
   else
@@ -265,7 +264,6 @@ int hs_create(const hs_config* cfg, hs_engine** out) {
     }
     cudaGetLastError();
     if (const char* k = getenv("HSGPU_MATCH_L2_LEVELS")) P.l2_keep_levels = atoi(k);
-    if (const char* k = getenv("HSGPU_MATCH_SERIAL_SPREAD")) P.serial_spread = atoi(k) != 0;
     P.tail_slots = 2 * n_sm;   // measured on B200 (148 SMs): 0 -> 179 us, 148 -> 178, 296 -> 176, 444 -> 178.5, 600 -> 181
   }
   if (const char* pw = getenv("HSGPU_HD_PPW")) e->hd_ppw = atoi(pw);

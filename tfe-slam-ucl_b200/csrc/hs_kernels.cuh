@@ -64,7 +64,6 @@ struct HsParams {
   const float4* hyp_pblk;           // ... WC == 2 instantiation: the stream's probability block planes (k_build_pblk) instead of val
   float* host_pose_out;             // non-NULL: the caller's pinned poses_out [slot][3]; the matcher's tail writes the pose there too
   int n_sm;                         // SM count of the device
-  int serial_spread;                // k_match: 1 = the serial warps of the CTAs sharing an SM use two sub-partitions instead of one
   int reverse_order;                // k_raycast: this launch walks the slots from the last to the first
   int l2_keep_levels;               // bit l: the matcher's gathers on level l carry an L2 evict-last hint
   int tail_slots;                   // k_raycast: the last `tail_slots` slots of a launch are dispatched level-major
@@ -699,8 +698,7 @@ __global__ void __launch_bounds__(HS_MATCH_THREADS, (PPT > 0 && PPT <= 3) ? 7 : 
   // SMs breadth first and 148 = 0 mod 4, so the CTAs sharing an SM pick the SAME warp number and their serial warps share
   // one SM sub-partition (warp w issues from scheduler w mod 4), where their 4-cycle FADD chains interleave. Measured on
   // B200: spreading them over the four sub-partitions ((blockIdx + blockIdx / n_sm) & 3) costs 5-8 us per launch.
-  // P.serial_spread = 1: the CTAs of an SM alternate between two warp numbers (two sub-partitions carry the chains)
-  const int sw = (P.serial_spread ? (blockIdx.x ^ ((blockIdx.x / (unsigned)P.n_sm) & 1u)) : blockIdx.x) & ((blockDim.x >> 5) - 1);
+  const int sw = blockIdx.x & ((blockDim.x >> 5) - 1);
   const bool serial = (tid >> 5) == sw, leader = tid == (sw << 5);
   const bool hyp = P.hyp_pose != nullptr;
   const int s = hyp ? P.hyp_stream : hs_slot_stream(stream_ids, slot);
