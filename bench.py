@@ -66,6 +66,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU work for the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the sub-records of the other BASELINE configurations")
+    ap.add_argument("--clock-interval-ms", type=int, default=20, help="nvidia-smi sampling period during the timed legs")
     ap.add_argument("--only-config", default=None, help="run one sub-record alone and print it (c3 | c4 | c5): for ncu captures")
     return ap.parse_args()
 
@@ -81,9 +82,10 @@ def measured_peak():
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, interval_ms=20):
         super().__init__(daemon=True)
         self.gpu = gpu_index
+        self.interval_ms = max(int(interval_ms), 5)
         self.samples = []
         self.stop_flag = threading.Event()
         self.proc = None
@@ -92,7 +94,7 @@ class ClockSampler(threading.Thread):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "20"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", str(self.interval_ms)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 if self.stop_flag.is_set():
@@ -436,7 +438,7 @@ def main():
     barrier()
     st0 = eng.stats()
     eng.profile_enable(PROF_EVERY)   # CUDA events around the kernels of every PROF_EVERY-th timed step
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, args.clock_interval_ms)
     sampler.start()
     time.sleep(0.3)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
