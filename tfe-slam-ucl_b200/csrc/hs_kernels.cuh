@@ -1995,9 +1995,16 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_raycast(HsParams P, int n
               const int yy = hs_udiv_small(k, pitch, xx);   // k < 2^18, pitch < 2^15: exact
               hs_free_hits_end_cell(hkeys, hvals, hash_mask, log2_hash, (yy + yb0) * W + (xx + x0), beam);
             }
-            k += off_a;
-            err += db;
-            if (err >= da) { k += off_b; err -= da; }
+            // bresenham2D's update (OccGridMapBase.h:252-258) as predicated adds: 5 instructions, 2 of them on the alu pipe --
+            // the compiler makes add / compare / select / select / subtract / 3-input add (4 alu) of the C form, and the alu pipe
+            // (one warp instruction per 2 cycles per scheduler) is the walk's busiest: 160.9 -> 159.5 us per launch, same box
+            asm volatile("{ .reg .pred p;\n\t"
+                         "add.s32 %1, %1, %2;\n\t"       // err += db
+                         "add.s32 %0, %0, %4;\n\t"       // k += off_a
+                         "setp.ge.s32 p, %1, %3;\n\t"
+                         "@p sub.s32 %1, %1, %3;\n\t"    // err -= da
+                         "@p add.s32 %0, %0, %5;\n\t"    // k += off_b
+                         "}" : "+r"(k), "+r"(err) : "r"(db), "r"(da), "r"(off_a), "r"(off_b));
           }
           rem -= steps;
           if (rem == 0 && j + 1 < j1) {
