@@ -2061,14 +2061,26 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_raycast(HsParams P, int n
           const float4 a = hs_lds_f4(addlut_s + (bits << 4));   // (bit i ? f : -0.0f) for the quad's four cells: one 16-byte shared load instead of 8 selects
           asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(valq + gq), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w) : "memory");
           if (HS_DBG(P, 8)) {   // timing experiment (wrong markers): no free-marker stores
-          } else if (bits == 0xFu || HS_DBG(P, 64)) {   // bit 6, timing experiment (wrong markers): every quad as one store
-            hs_stg_u32(mkq + gq, bf4);
           } else {
+            // the quad's marker address is formed ONCE (left to itself the compiler re-derives the 64-bit sum in front of every
+            // predicated byte store: 3 instructions per byte, 12 % of the kernel's instructions), the byte stores of a partly
+            // marked quad are four predicated stores at immediate offsets
             uint8_t* mq = mkq + gq;
-            if (bits & 1u) hs_stg_u8(mq, b_free);
-            if (bits & 2u) hs_stg_u8(mq + 1, b_free);
-            if (bits & 4u) hs_stg_u8(mq + 2, b_free);
-            if (bits & 8u) hs_stg_u8(mq + 3, b_free);
+            asm volatile("" : "+l"(mq));
+            if (bits == 0xFu || HS_DBG(P, 64)) {   // bit 6, timing experiment (wrong markers): every quad as one store
+              hs_stg_u32(mq, bf4);
+            } else {
+              asm volatile("{ .reg .pred p0, p1, p2, p3; .reg .b32 t;\n\t"
+                           "and.b32 t, %1, 1; setp.ne.u32 p0, t, 0;\n\t"
+                           "and.b32 t, %1, 2; setp.ne.u32 p1, t, 0;\n\t"
+                           "and.b32 t, %1, 4; setp.ne.u32 p2, t, 0;\n\t"
+                           "and.b32 t, %1, 8; setp.ne.u32 p3, t, 0;\n\t"
+                           "@p0 st.global.u8 [%0], %2;\n\t"
+                           "@p1 st.global.u8 [%0+1], %2;\n\t"
+                           "@p2 st.global.u8 [%0+2], %2;\n\t"
+                           "@p3 st.global.u8 [%0+3], %2;\n\t"
+                           "}" ::"l"(mq), "r"(bits), "r"(b_free) : "memory");
+            }
           }
         }
         c += d_c; ni += ni_step; gq += gq_step;
