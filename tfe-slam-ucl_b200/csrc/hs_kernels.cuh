@@ -702,13 +702,23 @@ __global__ void __launch_bounds__(HS_MATCH_THREADS, (PPT > 0 && PPT <= 3) ? 7 : 
   const bool serial = (tid >> 5) == sw, leader = tid == (sw << 5);
   const bool hyp = P.hyp_pose != nullptr;
   const int s = hyp ? P.hyp_stream : hs_slot_stream(stream_ids, slot);
-  int n = counts[hyp ? 0 : slot];
-  n = n < 0 ? 0 : (n > P.max_points ? P.max_points : n);
   // point i = i0 + j * istride of the scan is this thread's j-th. (Measured on B200: leaving the serial warp without points,
   // so that its SM sub-partition only carries the latency-critical chains, and giving the other three warps 4 points per
   // thread, costs 18 us per launch -- the points phase needs all four sub-partitions.)
   const int i0 = tid, istride = (int)blockDim.x;
   const float2* pts = points + (hyp ? (size_t)0 : (size_t)slot * P.max_points);
+  // register-resident points: requested BEFORE the count is known (a row always has max_points slots), so that the prologue
+  // is one memory round trip (count, hint and points together) instead of count -> points
+  float2 preg[PPT > 0 ? PPT : 1];
+  if (PPT > 0 && !P.stage_pts) {
+#pragma unroll
+    for (int j = 0; j < (PPT > 0 ? PPT : 1); ++j) {
+      const int i = i0 + j * istride;
+      preg[j] = i < P.max_points ? pts[i] : make_float2(0.f, 0.f);
+    }
+  }
+  int n = counts[hyp ? 0 : slot];
+  n = n < 0 ? 0 : (n > P.max_points ? P.max_points : n);
   if (P.stage_pts) {   // zero-copy input: fetch this scan from the caller's pinned host buffer once
     if (P.stage_cnt && tid == 0) P.stage_cnt[slot] = n;
     float2* stg = P.stage_pts + (size_t)slot * P.max_points;
@@ -717,17 +727,39 @@ __global__ void __launch_bounds__(HS_MATCH_THREADS, (PPT > 0 && PPT <= 3) ? 7 : 
     for (int i = tid; i < n_fetch; i += blockDim.x) stg[i] = pts[i];
     __syncthreads();
     pts = stg;
+    if (PPT > 0) {
+#pragma unroll
+      for (int j = 0; j < (PPT > 0 ? PPT : 1); ++j) {
+        const int i = i0 + j * istride;
+        preg[j] = i < n ? pts[i] : make_float2(0.f, 0.f);
+      }
+    }
   }
   const bool mwm = mwm_flags ? (mwm_flags[slot] != 0) : false;
   float wx, wy, wth;
   if (hints) { wx = hints[3 * slot]; wy = hints[3 * slot + 1]; wth = hints[3 * slot + 2]; }
   else { wx = P.last_pose[3 * s]; wy = P.last_pose[3 * s + 1]; wth = P.last_pose[3 * s + 2]; }
+  if (PPT > 0) {
+#pragma unroll
+    for (int j = 0; j < (PPT > 0 ? PPT : 1); ++j)
+      if (i0 + j * istride >= n) preg[j] = make_float2(0.f, 0.f);
+  }
 
   if (!mwm) {
     // dataContainers[level-1].setFrom(dataContainer, 2^-level) (MapRepMultiMap.h:127): keep the level-0
     // points of the last matched scan; the power-of-two factor is applied (exactly) where they are used.
     float2* cp = reinterpret_cast<float2*>(P.coarse_pts) + (size_t)s * P.max_points;
-    if (!hyp) for (int i = tid; i < n; i += blockDim.x) cp[i] = pts[i];
+    if (!hyp) {
+      if (PPT > 0) {
+#pragma unroll
+        for (int j = 0; j < (PPT > 0 ? PPT : 1); ++j) {
+          const int i = i0 + j * istride;
+          if (i < n) cp[i] = preg[j];
+        }
+      } else {
+        for (int i = tid; i < n; i += blockDim.x) cp[i] = pts[i];
+      }
+    }
     if (tid == 0 && !hyp) {
       P.coarse_cnt[s] = n;
       float2 o = origos ? origos[slot] : make_float2(0.f, 0.f);
@@ -740,15 +772,7 @@ __global__ void __launch_bounds__(HS_MATCH_THREADS, (PPT > 0 && PPT <= 3) ? 7 : 
       unsigned clamps = 0;
       HsMatchTimer mt;
       mt.begin(P.dbg_times);
-      float2 preg[PPT > 0 ? PPT : 1];
       HsCellCache cache[PPT > 0 ? PPT : 1];
-      if (PPT > 0) {
-#pragma unroll
-        for (int j = 0; j < (PPT > 0 ? PPT : 1); ++j) {
-          const int i = i0 + j * istride;
-          preg[j] = i < n ? pts[i] : make_float2(0.f, 0.f);
-        }
-      }
       for (int level = P.n_levels - 1; level >= 0; --level) {
         const HsLevel& Lc = P.lv[level];   // constant bank, indexed by a run-time level: only touched here, once per level
         float ex = 0.f, ey = 0.f, eth = wth;
