@@ -1533,7 +1533,7 @@ __device__ __forceinline__ HsBeam hs_make_beam(const HsLevel& L, int bx, int by,
 struct HsBeamRec {
   int kend;                    // end cell offset in the grid
   unsigned short da, db;       // abs_da (0 marks a dropped beam), abs_db
-  unsigned int flags;          // bit0: dominant axis is x, bit1: step along a is +, bit2: step along b is +
+  unsigned int flags;          // bit0: dominant axis is x, bit1: step along a is +, bit2: step along b is +, bits 3..: end row
 };
 
 // Walk record: one per end-cell owner beam, everything the free-cell walk needs in one 16-byte shared load.
@@ -1697,13 +1697,13 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_raycast(HsParams P, int n
     // this launch covers levels [level_first, level_first + level_count) of every slot
     const int n_tail = min(n_slots, P.tail_slots), n_head = n_slots - n_tail;
     int local;
+    // (hs_udiv_small: the generic 32-bit division is ~35 instructions, and every thread of the launch runs this)
     if ((int)blockIdx.x < n_head * level_count) {
-      local = blockIdx.x / level_count;
-      level = blockIdx.x - local * level_count;
+      local = hs_udiv_small((int)blockIdx.x, level_count, level);
     } else {
-      const int r = blockIdx.x - n_head * level_count;
-      level = r / n_tail;
-      local = n_head + (r - level * n_tail);
+      int rem;
+      level = hs_udiv_small((int)blockIdx.x - n_head * level_count, n_tail, rem);
+      local = n_head + rem;
     }
     if (local >= n_slots || level >= level_count) return;
     level += level_first;
@@ -1799,7 +1799,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_raycast(HsParams P, int n
       HsBeam b = hs_make_beam(L, bx, by, mpx, mpy, sn, cs, p.x * pf, p.y * pf);
       HsBeamRec r;
       r.kend = b.kend; r.da = 0; r.db = (unsigned short)b.abs_db;
-      r.flags = (unsigned)((b.a_is_x ? 1 : 0) | (b.sa > 0 ? 2 : 0) | (b.sb > 0 ? 4 : 0));
+      r.flags = (unsigned)((b.a_is_x ? 1 : 0) | (b.sa > 0 ? 2 : 0) | (b.sb > 0 ? 4 : 0)) | ((unsigned)b.ey << 3);   // + the end row: no division by W later
       if (b.valid) {
         visits += b.abs_da + 1u;
         r.da = (unsigned short)b.abs_da;
@@ -1834,8 +1834,9 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_raycast(HsParams P, int n
   const int bh = y1 - y0 + 1;
   const int pw = (((x1 - x0) >> 4) + 1) | 1;   // 16-cell words per map row
   const int pitch = pw << 4;                   // cells per map row
-  const int band_rows = min(bh, MAP_CELLS / pitch);   // >= 1: hs_create limits the grid width
-  const int n_bands = (bh + band_rows - 1) / band_rows;
+  int div_rem;
+  const int band_rows = min(bh, hs_udiv_small(MAP_CELLS, pitch, div_rem));   // >= 1: hs_create limits the grid width
+  const int n_bands = hs_udiv_small(bh + band_rows - 1, band_rows, div_rem);
 
   const bool single_band = n_bands == 1;
   const int log2_seg = level == 0 ? (log2_seg_levels & 0xFF) : (log2_seg_levels >> 8);   // per level: fine grid / coarse grids
@@ -1892,7 +1893,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_raycast(HsParams P, int n
       if (single_band) {   // the whole trace lies in the one band; mark the end cell in the (already cleared) map
         tlo[pos] = 0;
         tlen[pos] = r.da;
-        const int ey = r.kend / W, ex = r.kend - ey * W;
+        const int ey = (int)(r.flags >> 3), ex = r.kend - ey * W;
         const int kb = (ey - y0) * pitch + (ex - x0);
         atomicOr(&cmap[kb >> 4], 0x10000u << (kb & 15));
       }
@@ -1928,8 +1929,8 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_raycast(HsParams P, int n
       if (wi < n_walk) {
         const HsWalkRec w = walk[wi];
         const int da = (int)(w.dadb & 0xFFFFu), db = (int)(w.dadb >> 16);
-        const int kend = beams[w.beam & 0x3FFFFFFF].kend;
-        const int ey = kend / W, ex = kend - ey * W;
+        const HsBeamRec br = beams[w.beam & 0x3FFFFFFF];
+        const int ey = (int)(br.flags >> 3), ex = br.kend - ey * W;
         if (ey >= yb0 && ey <= yb1) {
           const int kb = (ey - yb0) * pitch + (ex - x0);
           atomicOr(&cmap[kb >> 4], 0x10000u << (kb & 15));
