@@ -1686,6 +1686,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_raycast(HsParams P, int n
   __shared__ int s_items;
   __shared__ int s_wsum[32];
   __shared__ unsigned s_visits;
+  __shared__ unsigned s_inv_pitch;   // floor((2^32 - 1) / pitch) of the cell map
 
   // slot-major launch order: the long fine-grid CTAs and the short coarse-grid CTAs of a scan are dispatched together, which
   // keeps the mix of shared-memory-bound (walk) and HBM-bound (sweep) work on every SM even (measured: level-major order
@@ -1838,6 +1839,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_raycast(HsParams P, int n
   const int band_rows = min(bh, hs_udiv_small(MAP_CELLS, pitch, div_rem));   // >= 1: hs_create limits the grid width
   const int n_bands = hs_udiv_small(bh + band_rows - 1, band_rows, div_rem);
 
+  if (threadIdx.x == 0) s_inv_pitch = 0xFFFFFFFFu / (unsigned)pitch;   // read after the barrier behind phase A3
   const bool single_band = n_bands == 1;
   const int log2_seg = level == 0 ? (log2_seg_levels & 0xFF) : (log2_seg_levels >> 8);   // per level: fine grid / coarse grids
   const int seg = 1 << log2_seg;
@@ -2003,8 +2005,10 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_raycast(HsParams P, int n
         int t0 = (SINGLE ? 0 : (int)tlo[p]) + s_off;
         int rem = (SINGLE ? da : (int)tlen[p]) - s_off;
         int e0 = (da >> 1) + t0 * db;
-        int q0 = e0 / da;
-        int k = k0 + t0 * off_a + q0 * off_b, err = e0 - q0 * da;
+        int err;
+        int q0 = e0 < (1 << 22) ? hs_udiv_small(e0, da, err) : e0 / da;   // (the generic division: hi-res grids with long, steep traces only)
+        int k = k0 + t0 * off_a + q0 * off_b;
+        err = e0 - q0 * da;
         for (; j < j1; ++j) {
           const int steps = min(seg, rem);
           for (int t = 0; t < steps; ++t) {
@@ -2015,9 +2019,12 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_raycast(HsParams P, int n
             const unsigned waddr = cmap_s + (((unsigned)k >> 4) << 2);
             const unsigned fbit = 1u << ((unsigned)k & 15u);
             const unsigned word = hs_atoms_or(waddr, fbit);
-            if (word & (fbit << 16)) {   // the free trace crosses a cell that is some beam's end point (rare)
-              int xx;
-              const int yy = hs_udiv_small(k, pitch, xx);   // k < 2^18, pitch < 2^15: exact
+            if (word & (fbit << 16)) {   // the free trace crosses a cell that is some beam's end point (one warp step in five)
+              // k -> (row, column) of the map: multiplication by floor(2^32 / pitch) and one correction (k < 2^20: the product's
+              // error is below one)
+              int yy = (int)__umulhi((unsigned)k, s_inv_pitch);
+              int xx = k - yy * pitch;
+              if (xx >= pitch) { ++yy; xx -= pitch; }
               hs_free_hits_end_cell(hkeys, hvals, hash_mask, log2_hash, (yy + yb0) * W + (xx + x0), beam);
             }
             // bresenham2D's update (OccGridMapBase.h:252-258) as predicated adds: 5 instructions, 2 of them on the alu pipe --
@@ -2070,7 +2077,8 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_raycast(HsParams P, int n
       const unsigned bf4 = b_free * 0x01010101u;
       // a thread's quads are T apart in the row-major list; its position advances incrementally: c = quad in the row,
       // ni = nibble index into the cell map (row pitch pw*4 nibbles), gq = cell offset of the quad in the grid
-      const int d_ry = T / qpr, d_c = T - d_ry * qpr;   // one stride of T quads, as (rows, quads)
+      int d_c;
+      const int d_ry = hs_udiv_small(T, qpr, d_c);   // one stride of T quads, as (rows, quads)
       const int ni_step = d_ry * (pw << 2) + d_c, gq_step = d_ry * W + (d_c << 2);
       const int ni_wrap = (pw << 2) - qpr, gq_wrap = W - (qpr << 2);
       int c;
