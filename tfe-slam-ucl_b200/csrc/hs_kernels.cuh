@@ -1848,6 +1848,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_raycast(HsParams P, int n
   // phase A3: walk list = the owner beam of every end cell. Beams that share an end cell have identical traces (same
   // start, same end), and the owner -- the smallest index -- is the one that decides every "free came first" question.
   float v_end = 0.0f;   // log-odds of the end cell owned by beam threadIdx.x (first pass of A3)
+  int my_pos = 0, my_seg0 = 0, my_nseg = 0;   // this thread's owner beam of the first pass: list position, first segment, segments
   for (int i0 = 0; i0 < n; i0 += T) {
     const int i = i0 + threadIdx.x;
     bool owner = false;
@@ -1888,13 +1889,12 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_raycast(HsParams P, int n
       w.seg_start = (int)(unsigned)(base & 0xFFFFFFFFULL) + incl - nseg;
       const int pos = (int)(base >> 32) + __popc(m & ((1u << lane) - 1u));
       walk[pos] = w;
+      if (i0 == 0) { my_pos = pos; my_seg0 = w.seg_start; my_nseg = nseg; }
       // phase C needs this end cell's log-odds. Nothing else touches an end cell during the scan (the sweep only adds -0.0f
       // to it), so the load is issued now and consumed after the walk and the sweep: its latency never shows.
       if (i0 == 0) v_end = __ldcg(val + r.kend);
       else asm volatile("prefetch.global.L2 [%0];" ::"l"(val + r.kend));
       if (single_band) {   // the whole trace lies in the one band; mark the end cell in the (already cleared) map
-        tlo[pos] = 0;
-        tlen[pos] = r.da;
         const int ey = (int)(r.flags >> 3), ex = r.kend - ey * W;
         const int kb = (ey - y0) * pitch + (ex - x0);
         atomicOr(&cmap[kb >> 4], 0x10000u << (kb & 15));
@@ -1903,6 +1903,20 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_raycast(HsParams P, int n
   }
   __syncthreads();
   const int n_walk = (int)(s_alloc >> 32);
+  // Start table (single band, one pass of A3): walk slot u begins at segment u * per, and the owner beam that holds that segment
+  // leaves its list position there -- instead of every thread binary-searching the walk list for it (5 % of the kernel's
+  // instructions). tlo / tlen (contiguous, 2 * max_points entries) are not used by a single-band scan.
+  unsigned short* wstart = tlo;
+  const bool fast_start = single_band && n <= T && 2 * P.max_points >= T;
+  if (fast_start) {
+    const int per0 = ((int)(unsigned)(s_alloc & 0xFFFFFFFFULL) + T - 1) / T;
+    if (my_nseg > 0) {
+      int rem;
+      int u = hs_udiv_small(my_seg0 + per0 - 1, per0, rem);   // first slot that starts at or behind this beam's first segment
+      for (int js = u * per0; js < my_seg0 + my_nseg; js += per0, ++u) wstart[u] = (unsigned short)my_pos;
+    }
+    __syncthreads();
+  }
   hs_stamp(P, 2);
 
   const int warp = threadIdx.x >> 5, n_warps = T >> 5;
@@ -1988,13 +2002,18 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_raycast(HsParams P, int n
       const int per = (n_items + T - 1) / T;
       // neighbouring lanes take segments ~37 beams apart: lanes that walk adjacent beams at the same radius would hit
       // the same 16-cell map words in the same instruction and serialise in the shared-memory atomics
-      int j = (int)((threadIdx.x * 37u) % (unsigned)T) * per;
+      const int uslot = (int)((threadIdx.x * 37u) % (unsigned)T);
+      int j = uslot * per;
       const int j1 = min(j + per, n_items);
       if (j < j1) {
         int lo = 0, hi = n_walk - 1;       // largest p with walk[p].seg_start <= j
-        while (lo < hi) {
-          const int mid = (lo + hi + 1) >> 1;
-          if (walk[mid].seg_start <= j) lo = mid; else hi = mid - 1;
+        if (SINGLE && fast_start) {
+          lo = (int)wstart[uslot];
+        } else {
+          while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (walk[mid].seg_start <= j) lo = mid; else hi = mid - 1;
+          }
         }
         int p = lo;
         HsWalkRec w = walk[p];
