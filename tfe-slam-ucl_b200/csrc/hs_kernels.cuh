@@ -2036,7 +2036,8 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_raycast(HsParams P, int n
             // per step, and near the sensor, where most cells are already marked by other beams, nearly every warp iteration ran
             // both sides of the test: 27 lanes -> 16 + 11, ncu.) A free bit that lands on an end cell is masked out by the sweep.
             const unsigned waddr = cmap_s + (((unsigned)k >> 4) << 2);
-            const unsigned fbit = 1u << ((unsigned)k & 15u);
+            unsigned fbit;   // 1 << (k & 15) as a one-bit mask (BMSK: no register for the constant 1)
+            asm("bmsk.clamp.b32 %0, %1, 1;" : "=r"(fbit) : "r"((unsigned)k & 15u));
             const unsigned word = hs_atoms_or(waddr, fbit);
             if (word & (fbit << 16)) {   // the free trace crosses a cell that is some beam's end point (one warp step in five)
               // k -> (row, column) of the map: multiplication by floor(2^32 / pitch) and one correction (k < 2^20: the product's
