@@ -1700,7 +1700,15 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_raycast(HsParams P, int n
     int local;
     // (hs_udiv_small: the generic 32-bit division is ~35 instructions, and every thread of the launch runs this)
     if ((int)blockIdx.x < n_head * level_count) {
-      local = hs_udiv_small((int)blockIdx.x, level_count, level);
+      const unsigned b = blockIdx.x;   // level_count <= HS_MAX_LEVELS: divisions by constants (multiply-high)
+      switch (level_count) {
+        case 1: local = (int)b; break;
+        case 2: local = (int)(b >> 1); break;
+        case 3: local = (int)(b / 3u); break;
+        case 4: local = (int)(b >> 2); break;
+        default: local = (int)(b / (unsigned)level_count); break;
+      }
+      level = (int)b - local * level_count;
     } else {
       int rem;
       level = hs_udiv_small((int)blockIdx.x - n_head * level_count, n_tail, rem);
@@ -1835,9 +1843,12 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_raycast(HsParams P, int n
   const int bh = y1 - y0 + 1;
   const int pw = (((x1 - x0) >> 4) + 1) | 1;   // 16-cell words per map row
   const int pitch = pw << 4;                   // cells per map row
-  int div_rem;
-  const int band_rows = min(bh, hs_udiv_small(MAP_CELLS, pitch, div_rem));   // >= 1: hs_create limits the grid width
-  const int n_bands = hs_udiv_small(bh + band_rows - 1, band_rows, div_rem);
+  int band_rows = bh, n_bands = 1;
+  if (bh * pitch > MAP_CELLS) {   // (rare for 360-beam scans: the divisions are skipped)
+    int div_rem;
+    band_rows = min(bh, hs_udiv_small(MAP_CELLS, pitch, div_rem));   // >= 1: hs_create limits the grid width
+    n_bands = hs_udiv_small(bh + band_rows - 1, band_rows, div_rem);
+  }
 
   if (threadIdx.x == 0) s_inv_pitch = 0xFFFFFFFFu / (unsigned)pitch;   // read after the barrier behind phase A3
   const bool single_band = n_bands == 1;
