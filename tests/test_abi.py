@@ -94,3 +94,15 @@ def test_product_library_holds_no_workload_generator(hs):
             "maps = open('/proc/self/maps').read(); assert 'libhsgpu' not in maps and 'libcudart' not in maps; print(int(c.sum()))" % ROOT)
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
     assert res.returncode == 0 and int(res.stdout.strip()) > 100, res.stderr
+
+
+def test_profile_phase_anchors_resolve():
+    """tests/tools/ncu_phase_tables.py finds the phases of k_match / k_raycast by anchor strings in hs_kernels.cuh: the
+    anchors must still be there (and in order) after an edit of the kernels, or the committed phase tables cannot be regenerated."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ncu_phase_tables", os.path.join(ROOT, "tests", "tools", "ncu_phase_tables.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)      # resolves every anchor at import (SystemExit if one is missing)
+    for name, table in (("k_raycast", mod.ray), ("k_match", mod.match)):
+        for phase, lo, hi in table:
+            assert 0 < lo <= hi, (name, phase, lo, hi)

@@ -53,7 +53,14 @@ match = [("points step 1 (transform / key / ballot)", pp - 1, dense - 1), ("poin
          ("points step 3 (bilinear / products)", s3, ev - 5), ("evaluation glue + barrier", ev, chain - 1), ("strict chain", chain, gn - 4),
          ("Gauss-Newton step", gn, tail - 4), ("tail", tail, km - 14), ("kernel body (prologue / level loop / barriers)", km, kmend),
          ("store products", sp, sp + 11), ("small helpers", hl, hl_end)]
-G = os.path.join(ROOT, "gpurun_out")
-run(os.path.join(G, "r02_c2.ncu-rep"), "k_raycast", "k_raycastILi384ELi32768ELi4E", "r02_c2_k_raycast_lines.md", ray)
-run(os.path.join(G, "r02_c2.ncu-rep"), "k_match", "k_matchILb1ELi3ELi1ELi388E", "r02_c2_k_match_lines.md", match)
-run(os.path.join(G, "r02_c3.ncu-rep"), "k_raycast", "k_raycastILi1024ELi147456ELi1E", "r02_c3_k_raycast_lines.md", ray)
+
+
+def main():
+    G = os.path.join(ROOT, "gpurun_out")
+    run(os.path.join(G, "r02_c2.ncu-rep"), "k_raycast", "k_raycastILi384ELi32768ELi4E", "r02_c2_k_raycast_lines.md", ray)
+    run(os.path.join(G, "r02_c2.ncu-rep"), "k_match", "k_matchILb1ELi3ELi1ELi388E", "r02_c2_k_match_lines.md", match)
+    run(os.path.join(G, "r02_c3.ncu-rep"), "k_raycast", "k_raycastILi1024ELi147456ELi1E", "r02_c3_k_raycast_lines.md", ray)
+
+
+if __name__ == "__main__":
+    main()
